@@ -105,6 +105,19 @@ class _KKT:
     def ok(self):
         return self.inertia == (self.n, self.mc, 0)
 
+    def _ldl_solve(self, b):
+        if not hasattr(self, '_Lp'):
+            self._Lp = np.ascontiguousarray(self.lu[self.perm])      # unit lower triangular
+            self._dinv = np.linalg.inv(self.d)                       # block diagonal (1x1 / 2x2)
+        y = sla.solve_triangular(self._Lp, b[self.perm], lower=True, unit_diagonal=True,
+                                 check_finite=False)
+        z = self._dinv @ y
+        xp = sla.solve_triangular(self._Lp.T, z, lower=False, unit_diagonal=True,
+                                  check_finite=False)
+        out = np.empty_like(b)
+        out[self.perm] = xp
+        return out
+
     def solve(self, rx, rs, rc, rd):
         """Solve the full 4-block system
             (H+dw) dx + Jc' dyc + Jd' dyd = rx
@@ -115,9 +128,9 @@ class _KKT:
         # => (H+dw + Jd' D Jd) dx + Jc' dyc = rx + Jd'(D rd + rs)
         r1 = rx + self.Jd.T @ (self.D * rd + rs)
         rhs = np.concatenate([r1, rc])
-        sol = np.linalg.solve(self.K, rhs)
+        sol = self._ldl_solve(rhs)
         # one step of iterative refinement (IPOPT refines too)
-        sol += np.linalg.solve(self.K, rhs - self.K @ sol)
+        sol += self._ldl_solve(rhs - self.K @ sol)
         dx, dyc = sol[:self.n], sol[self.n:]
         ds = self.Jd @ dx - rd
         dyd = self.D * ds - rs
