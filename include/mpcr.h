@@ -1,0 +1,133 @@
+/* mpcr.h - C ABI of the B200-native batched NMPC solver.
+ *
+ * Drop-in boundary for the hot path of AlexGisi/mpc-racing (reference paths are
+ * relative to that repository):
+ *
+ *   mpcr_solve_batch   replaces  control/MPC.py:10-181  (MPC.__init__: build the
+ *                      Opti NLP, solve it with IPOPT) and control/MPC.py:183-184
+ *                      (MPC.solution()), for B problems at once.  Argument
+ *                      meaning follows the constructor: state0 -> x0 (+ u_prev =
+ *                      state0.throttle/steer, NaN = None), s0, centerline_{x,y}_
+ *                      poly_coeffs -> cx/cy (5 coefficients, highest order first,
+ *                      absolute progress), max_error, runtime_params -> params,
+ *                      last_controls -> u_warm, Ts / N -> mpcr_config.
+ *   mpcr_config        mirrors control/ControllerParameters.py:4-32 and the IPOPT
+ *                      options of control/MPC.py:152-161.
+ *   mpcr_track_*       replace splines/ParameterizedLine.py:19-105 (Gx..ddGy,
+ *                      x/y_as_coeffs, projection) and
+ *                      splines/ParameterizedCenterline.py:61-91 (lookup_error,
+ *                      error_sign) for batches of queries.
+ *
+ * All arrays are fp64, row-major [B, ...], caller-owned.  No exceptions cross the
+ * boundary: every function returns 0 on success or a negative error code and
+ * mpcr_last_error() gives the text.  Per-problem solver outcomes are reported
+ * only through status[] (>= 0 is what CasADi's Opti treats as success).
+ * There is no CPU fallback: without a CUDA device mpcr_create fails.
+ */
+#ifndef MPCR_H_
+#define MPCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCR_VERSION 100
+
+/* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
+ * models/BlendedBicycleModel.py:23-46 blend of the two) */
+#define MPCR_MODEL_DYNAMIC 0
+#define MPCR_MODEL_KINEMATIC 1
+#define MPCR_MODEL_BLENDED 2
+
+/* per-problem status codes */
+#define MPCR_SOLVE_SUCCEEDED 0
+#define MPCR_SOLVED_TO_ACCEPTABLE_LEVEL 1
+#define MPCR_MAXITER_EXCEEDED (-1)
+#define MPCR_RESTORATION_FAILED (-2)
+#define MPCR_ERROR_IN_STEP_COMPUTATION (-3)
+#define MPCR_INVALID_NUMBER (-4)
+
+/* function return codes */
+#define MPCR_OK 0
+#define MPCR_ERR_INVALID_ARG (-1)
+#define MPCR_ERR_CUDA (-2)
+#define MPCR_ERR_NO_DEVICE (-3)
+
+typedef struct mpcr_config {
+  /* problem shape */
+  int32_t N;                 /* horizon, 1..32 (FixedControllerParameters.N = 30) */
+  int32_t model;             /* MPCR_MODEL_* */
+  int32_t wrap_constraint;   /* keep the i=0 wrap rows of control/MPC.py:142-143 (1 = parity) */
+  int32_t lane_constraint;   /* enable the lane row commented out at control/MPC.py:135 */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t pointers_on_device;/* 1: all array arguments are device pointers; 0: host pointers */
+  int32_t max_iter;          /* FixedControllerParameters.max_iter = 500 */
+  int32_t acceptable_iter;   /* IPOPT default 15 */
+  double Ts;                 /* FixedControllerParameters.Ts = 0.05 */
+  /* control/ControllerParameters.py:4-23 */
+  double lambda_s, alpha_L;
+  double min_steer, max_steer, min_throttle;
+  double max_steer_delta, min_steer_delta, max_throttle_delta, min_throttle_delta;
+  double q_v_max, v_max;
+  double min_s_delta;        /* control/MPC.py:59 */
+  /* control/ControllerParameters.py:26-32 */
+  double alpha_c, d_max, q_v_y, n_exp, beta_delta;
+  /* IPOPT options of control/MPC.py:152-161 + the termination defaults */
+  double tol, acceptable_tol;
+  double dual_inf_tol, constr_viol_tol, compl_inf_tol;
+  double mu_init;
+} mpcr_config;
+
+typedef struct mpcr_handle mpcr_handle;
+
+int mpcr_version(void);
+void mpcr_config_default(mpcr_config* cfg);
+int mpcr_create(const mpcr_config* cfg, mpcr_handle** out);
+int mpcr_destroy(mpcr_handle* h);
+const char* mpcr_last_error(mpcr_handle* h);
+
+/* length of one lam_g row in the output (13N+9, +N with the lane row); rows of
+ * problems without u_prev are zero-padded at the end */
+int mpcr_lam_g_stride(mpcr_handle* h);
+
+int mpcr_solve_batch(mpcr_handle* h, int B,
+                     const double* x0      /* [B,6] */,
+                     const double* u_prev  /* [B,2], NaN = None */,
+                     const double* s0      /* [B] */,
+                     const double* cx      /* [B,5] */,
+                     const double* cy      /* [B,5] */,
+                     const double* max_err /* [B] or NULL */,
+                     const double* params  /* [B,5] alpha_c,d_max,q_v_y,n,beta_delta or NULL */,
+                     const double* u_warm  /* [B,2,N] or NULL */,
+                     double* U             /* [B,2,N] */,
+                     double* X             /* [B,6,N+1] */,
+                     double* S             /* [B,N+1] */,
+                     double* eC            /* [B,N] */,
+                     double* eL            /* [B,N] */,
+                     double* lam_g         /* [B,stride] or NULL */,
+                     double* obj           /* [B] */,
+                     int32_t* status       /* [B] */,
+                     int32_t* iters        /* [B] */,
+                     void* cuda_stream     /* cudaStream_t or NULL */);
+
+/* Debug variant: also writes the per-iteration trace [B, max_iter+1, 8]
+ * (obj, E0, pr_inf, dual_inf, compl, mu, alpha, delta_w). */
+int mpcr_solve_batch_trace(mpcr_handle* h, int B, const double* x0, const double* u_prev,
+                           const double* s0, const double* cx, const double* cy,
+                           const double* max_err, const double* params, const double* u_warm,
+                           double* U, double* X, double* S, double* eC, double* eL,
+                           double* lam_g, double* obj, int32_t* status, int32_t* iters,
+                           double* trace, void* cuda_stream);
+
+/* Device time of the last solve kernel launch in milliseconds (CUDA events on
+ * the launch stream); blocks until that launch has finished. */
+int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
+/* Launch geometry of the solve kernel: blocks, warps per block, dynamic shared bytes. */
+int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCR_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of include/mpcr.h (the C ABI of libmpcr.so).
+
+This is the whole host<->device boundary: plain pointers and sizes, no torch
+types.  The library is built in-tree by ``__graft_entry__.build()`` /
+``mpc_racing_b200.build``; importing the solver without it fails loudly - there
+is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpcr.so")
+
+
+class MpcrConfig(C.Structure):
+    """Mirror of ``struct mpcr_config`` (include/mpcr.h)."""
+    _fields_ = [
+        ("N", C.c_int32), ("model", C.c_int32), ("wrap_constraint", C.c_int32),
+        ("lane_constraint", C.c_int32), ("device", C.c_int32),
+        ("pointers_on_device", C.c_int32), ("max_iter", C.c_int32),
+        ("acceptable_iter", C.c_int32),
+        ("Ts", C.c_double),
+        ("lambda_s", C.c_double), ("alpha_L", C.c_double),
+        ("min_steer", C.c_double), ("max_steer", C.c_double), ("min_throttle", C.c_double),
+        ("max_steer_delta", C.c_double), ("min_steer_delta", C.c_double),
+        ("max_throttle_delta", C.c_double), ("min_throttle_delta", C.c_double),
+        ("q_v_max", C.c_double), ("v_max", C.c_double), ("min_s_delta", C.c_double),
+        ("alpha_c", C.c_double), ("d_max", C.c_double), ("q_v_y", C.c_double),
+        ("n_exp", C.c_double), ("beta_delta", C.c_double),
+        ("tol", C.c_double), ("acceptable_tol", C.c_double),
+        ("dual_inf_tol", C.c_double), ("constr_viol_tol", C.c_double),
+        ("compl_inf_tol", C.c_double), ("mu_init", C.c_double),
+    ]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+SOLVE_ARGTYPES = [C.c_void_p] * 8 + [C.c_void_p] * 9   # 8 inputs, 9 outputs (raw addresses)
+
+# every symbol include/mpcr.h declares
+EXPORTED_SYMBOLS = [
+    "mpcr_version", "mpcr_config_default", "mpcr_create", "mpcr_destroy", "mpcr_last_error",
+    "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
+    "mpcr_launch_info",
+]
+
+_lib = None
+
+
+class MpcrError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Load libmpcr.so; raises MpcrError when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise MpcrError(
+            f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+            "g.build()').  mpc_racing_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    lib.mpcr_version.restype = C.c_int
+    lib.mpcr_config_default.argtypes = [C.POINTER(MpcrConfig)]
+    lib.mpcr_config_default.restype = None
+    lib.mpcr_create.argtypes = [C.POINTER(MpcrConfig), C.POINTER(C.c_void_p)]
+    lib.mpcr_create.restype = C.c_int
+    lib.mpcr_destroy.argtypes = [C.c_void_p]
+    lib.mpcr_destroy.restype = C.c_int
+    lib.mpcr_last_error.argtypes = [C.c_void_p]
+    lib.mpcr_last_error.restype = C.c_char_p
+    lib.mpcr_lam_g_stride.argtypes = [C.c_void_p]
+    lib.mpcr_lam_g_stride.restype = C.c_int
+    lib.mpcr_solve_batch.argtypes = [C.c_void_p, C.c_int] + SOLVE_ARGTYPES + [C.c_void_p]
+    lib.mpcr_solve_batch.restype = C.c_int
+    lib.mpcr_solve_batch_trace.argtypes = [C.c_void_p, C.c_int] + SOLVE_ARGTYPES + [C.c_void_p, C.c_void_p]
+    lib.mpcr_solve_batch_trace.restype = C.c_int
+    lib.mpcr_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.mpcr_last_kernel_ms.restype = C.c_int
+    lib.mpcr_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mpcr_launch_info.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_config(lib=None):
+    cfg = MpcrConfig()
+    (lib or load_library()).mpcr_config_default(C.byref(cfg))
+    return cfg

@@ -1,0 +1,1519 @@
+// One-problem-per-warp primal-dual interior-point solver for the racing NLP of
+// control/MPC.py (reference), replacing CasADi Opti + IPOPT + MUMPS.
+//
+//   * lane k (0..N-1) owns stage transition k: input u_k, successor state
+//     (x_{k+1}, s_{k+1}), the dynamics multipliers of rows x_{k+1} = f(x_k,u_k),
+//     and the slack rows of u_k / of the progress increment s_{k+1} - s_k;
+//   * the KKT system of every iteration is solved by a stage-wise Riccati
+//     recursion on the augmented state z = (x, s_hat, u_prev) in R^9 with input
+//     w = (thr, steer, ds) in R^3; the two wrap-around rate rows of
+//     control/MPC.py:142-143 (i = 0) couple stage 0 with stage N-1 and are
+//     handled as a rank-2 (Woodbury) correction with two extra right-hand sides;
+//   * algorithm, constants and option defaults: IPOPT (Waechter & Biegler 2006),
+//     the same restatement as oracle/ipm.py.
+//
+// The file is written against a tiny set of warp primitives (lane_id, shfl,
+// syncwarp) so that tests/emu can run the identical code on the CPU with a
+// fiber-based SIMT emulator (test infrastructure only - the product path is the
+// CUDA build).
+#pragma once
+#include "mpcr_model.cuh"
+
+namespace mpcr {
+
+// ---------------------------------------------------------------------------
+// warp primitives
+// ---------------------------------------------------------------------------
+#if defined(MPCR_EMU)
+MPCR_D int lane_id() { return emu::lane(); }
+MPCR_D double shfl(double v, int src) { return emu::shfl_f64(v, src); }
+MPCR_D int shfl_i(int v, int src) { return emu::shfl_i32(v, src); }
+MPCR_D void syncwarp() { emu::syncwarp(); }
+MPCR_D double shfl_xor(double v, int m) { return emu::shfl_f64(v, emu::lane() ^ m); }
+MPCR_D int shfl_xor_i(int v, int m) { return emu::shfl_i32(v, emu::lane() ^ m); }
+#else
+MPCR_D int lane_id() { return threadIdx.x & 31; }
+MPCR_D double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MPCR_D int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MPCR_D void syncwarp() { __syncwarp(); }
+MPCR_D double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+MPCR_D int shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+#endif
+
+MPCR_D double warp_sum(double v) {
+  for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+  return v;
+}
+MPCR_D double warp_max(double v) {
+  for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m));
+  return v;
+}
+MPCR_D double warp_min(double v) {
+  for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m));
+  return v;
+}
+MPCR_D bool warp_all(bool p) {
+  int v = p ? 1 : 0;
+  for (int m = 16; m > 0; m >>= 1) v &= shfl_xor_i(v, m);
+  return v != 0;
+}
+MPCR_D bool warp_any(bool p) { return !warp_all(!p); }
+// NaN-propagating max for finiteness checks
+MPCR_D bool finite_d(double v) { return v == v && fabs(v) < 1.0e300; }
+
+// ---------------------------------------------------------------------------
+// Per-warp workspace (shared memory)
+// ---------------------------------------------------------------------------
+// stage storage layout (doubles)
+constexpr int kOffA = 0;        // StageLin (21)
+constexpr int kOffB = 21;       // b = -c_{k+1}  (6)
+constexpr int kOffHs = 27;      // packed sparse stage Hessian (32)
+constexpr int kOffGs = 59;      // dense stage gradient over (z, w) (12)
+constexpr int kOffK = 71;       // feedback gain (3 x 9)
+constexpr int kOffKf = 98;      // feed-forward, 3 right-hand sides (3 x 3)
+constexpr int kOffRow = 107;    // row terms: R_tt, R_ss, D_lane, gC[3] (6)
+constexpr int kStride = 113;    // odd: conflict-free lane-parallel writes
+constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
+
+constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
+constexpr int kScratch = 81 + 108 + 144 + 27 + 27 + 36 + kMisc;
+MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
+
+struct WarpWs {
+  double* stage;  // [(N+1)][kStride]
+  double* P;      // [9][9]
+  double* T;      // [9][12]
+  double* G;      // [12][12]
+  double* pv;     // [3][9]
+  double* tv;     // [3][9]
+  double* gv;     // [3][12]
+  double* misc;   // [kMisc]
+  MPCR_HD void bind(double* base, int N) {
+    stage = base;
+    P = base + (N + 1) * kStride;
+    T = P + 81;
+    G = T + 108;
+    pv = G + 144;
+    tv = pv + 27;
+    gv = tv + 27;
+    misc = gv + 36;
+  }
+  MPCR_HD double* st(int k) const { return stage + k * kStride; }
+};
+
+// packed slot of the sparse stage Hessian for entry (row, col) of the 12x12
+// matrix over (X,Y,yaw,vx,vy,r,s,p_thr,p_st | thr,st,ds); -1 = structurally zero
+MPCR_HD int hs_slot(int r, int c) {
+  if (r > c) { int t = r; r = c; c = t; }
+  // (X, Y, s) block
+  if (r == 0 && c == 0) return 0;
+  if (r == 0 && c == 1) return 1;
+  if (r == 0 && c == 6) return 2;
+  if (r == 1 && c == 1) return 3;
+  if (r == 1 && c == 6) return 4;
+  if (r == 6 && c == 6) return 5;
+  // model block over (yaw, vx, vy, r, thr, st) -> indices 2,3,4,5,9,10
+  int mr = (r >= 2 && r <= 5) ? r - 2 : ((r == 9 || r == 10) ? r - 5 : -1);
+  int mc = (c >= 2 && c <= 5) ? c - 2 : ((c == 9 || c == 10) ? c - 5 : -1);
+  if (mr >= 0 && mc >= 0) return 6 + hm_idx(mr, mc);
+  if (r == 11 && c == 11) return 27;
+  if (r == 7 && c == 7) return 28;
+  if (r == 8 && c == 8) return 29;
+  if (r == 7 && c == 9) return 30;
+  if (r == 8 && c == 10) return 31;
+  return -1;
+}
+
+// out[c] = sum_k v[k] M[k][c],  M = [A B] (9 x 12) of one stage
+MPCR_D void mulM(const double* v, const double* A, double Ts, double* out) {
+  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15;
+  out[0] = v[0];
+  out[1] = v[1];
+  out[2] = aX[0] * v[0] + aY[0] * v[1] + v[2];
+  out[3] = aX[1] * v[0] + aY[1] * v[1] + d[0] * v[3] + d[3] * v[4] + d[6] * v[5];
+  out[4] = aX[2] * v[0] + aY[2] * v[1] + d[1] * v[3] + d[4] * v[4] + d[7] * v[5];
+  out[5] = Ts * v[2] + d[2] * v[3] + d[5] * v[4] + d[8] * v[5];
+  out[6] = v[6];
+  out[7] = 0.0;
+  out[8] = 0.0;
+  out[9] = bu[0] * v[3] + bu[2] * v[4] + bu[4] * v[5] + v[7];
+  out[10] = bu[1] * v[3] + bu[3] * v[4] + bu[5] * v[5] + v[8];
+  out[11] = v[6];
+}
+
+// zn = M [z; w]
+MPCR_D void applyM(const double* z, const double* w, const double* A, double Ts, double* zn) {
+  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15;
+  zn[0] = z[0] + aX[0] * z[2] + aX[1] * z[3] + aX[2] * z[4];
+  zn[1] = z[1] + aY[0] * z[2] + aY[1] * z[3] + aY[2] * z[4];
+  zn[2] = z[2] + Ts * z[5];
+  for (int i = 0; i < 3; ++i)
+    zn[3 + i] = d[3 * i] * z[3] + d[3 * i + 1] * z[4] + d[3 * i + 2] * z[5] + bu[2 * i] * w[0] +
+                bu[2 * i + 1] * w[1];
+  zn[6] = z[6] + w[2];
+  zn[7] = w[0];
+  zn[8] = w[1];
+}
+
+// slack rows owned by lane k
+enum Row : int {
+  kThrUb = 0, kThrLb = 1, kStUb = 2, kStLb = 3, kDThr = 4, kDSt = 5, kProg = 6,
+  kDThr0 = 7, kDSt0 = 8, kLane = 9
+};
+MPCR_HD bool row_hasL(int r) { return r != kThrUb && r != kStUb; }
+MPCR_HD bool row_hasU(int r) { return r != kThrLb && r != kStLb; }
+
+struct ProblemView {     // uniform over the warp
+  double x0[6];
+  double u_prev[2];
+  bool has_prev_thr, has_prev_st;
+  double s0;
+  double cx[5], cy[5];
+  double max_err;
+  const double* u_warm;  // [2][N] or null
+};
+
+struct SolveOut {        // pointers already offset to this problem
+  double* U; double* X; double* S; double* eC; double* eL; double* lam_g;
+  double* obj; int32_t* status; int32_t* iters; double* trace;
+};
+
+MPCR_HD int lam_g_len(const Config& c, bool has_thr, bool has_st) {
+  int N = c.N;
+  return 7 + N * (7 + (c.lane_con ? 1 : 0)) + 4 * N + (c.wrap ? 2 * N : 2 * (N - 1)) +
+         (has_thr ? 1 : 0) + (has_st ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------
+// The solver.  All members are per-lane registers unless noted "uniform".
+// ---------------------------------------------------------------------------
+struct WarpSolver {
+  const Config& cfg;
+  const Params& p;        // per-problem copy (GA sweeps override the runtime parameters)
+  const IpmOptions& o;
+  const ProblemView& pb;
+  WarpWs ws;
+  int lane, N;
+  bool act;
+  // primal iterate
+  double x[6], sh, u[2];
+  // multipliers (dynamics rows carry lam = dc * y_scaled; y0 uniform: x0 rows (6) + s0 row)
+  double lam[6], y0[7];
+  double dcs[6];            // gradient-based row scaling of the dynamics rows
+  double ddl;               // same for the lane row
+  double df;                // objective scaling (uniform)
+  // slack rows
+  unsigned rowmask;
+  double s[kNumRows], yd[kNumRows], vL[kNumRows], vU[kNumRows];
+  double rd[kNumRows];      // d_r(x) - s_r at the current iterate
+  double cres[6];           // x_{k+1} - f(x_k, u_k) at the current iterate
+  double fval;              // df * f(x) (uniform)
+  // search direction
+  double dx[6], dsh, du[2];
+  double mu, tau;
+  // filter: one entry per lane
+  double filt_th, filt_ph;
+  int filt_n;
+  int gslot[5];
+
+  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, double* wsbase)
+      : cfg(c), p(prm), o(c.o), pb(pv) {
+    lane = lane_id();
+    N = c.N;
+    act = lane < N;
+    ws.bind(wsbase, N);
+    for (int j = 0; j < 5; ++j) {
+      int e = lane + 32 * j;
+      int slot = 0xff;
+      if (e < 144) {
+        int rr = e / 12, cc = e % 12;
+        int sl = hs_slot(rr, cc);
+        slot = (sl < 0) ? 0xff : sl;
+        if (rr == cc && (rr <= 6 || rr == 9 || rr == 10)) slot |= 0x100;   // gets +delta_w
+      }
+      gslot[j] = slot;
+    }
+  }
+
+  MPCR_D bool on(int r) const { return (rowmask >> r) & 1u; }
+  MPCR_D int prev_lane() const { return lane == 0 ? N - 1 : lane - 1; }
+  MPCR_D int next_lane() const { return lane >= N - 1 ? 0 : lane + 1; }
+  MPCR_D double lo(int r) const { return ws.misc[r]; }
+  MPCR_D double hi(int r) const { return ws.misc[kNumRows + r]; }
+
+  // original (unrelaxed, unscaled-row) bounds of row r
+  MPCR_D void row_bounds(int r, double& l, double& h) const {
+    const double inf = 1.0e300;
+    switch (r) {
+      case kThrUb: l = -inf; h = p.d_max; break;
+      case kThrLb: l = p.min_throttle; h = inf; break;
+      case kStUb: l = -inf; h = p.max_steer; break;
+      case kStLb: l = p.min_steer; h = inf; break;
+      case kDThr: case kDThr0: l = p.min_throttle_delta; h = p.max_throttle_delta; break;
+      case kDSt: case kDSt0: l = p.min_steer_delta; h = p.max_steer_delta; break;
+      case kProg: l = p.min_s_delta; h = cfg.Ts * p.v_max; break;
+      default: l = -pb.max_err; h = pb.max_err; break;
+    }
+  }
+
+  // value of row r (scaled) at a point
+  MPCR_D double row_value(int r, const double* uu, const double* up, double shh, double shp,
+                          double eC) const {
+    switch (r) {
+      case kThrUb: case kThrLb: return uu[0];
+      case kStUb: case kStLb: return uu[1];
+      case kDThr: return uu[0] - up[0];
+      case kDSt: return uu[1] - up[1];
+      case kProg: return shh - shp;
+      case kDThr0: return uu[0] - pb.u_prev[0];
+      case kDSt0: return uu[1] - pb.u_prev[1];
+      default: return ddl * eC;
+    }
+  }
+  // J_r * (step), the row's linear form applied to a direction
+  MPCR_D double row_lin(int r, const double* duu, const double* dup, double dshh, double dshp,
+                        const double* dxy /* dX, dY of the lane's state */) const {
+    switch (r) {
+      case kThrUb: case kThrLb: case kDThr0: return duu[0];
+      case kStUb: case kStLb: case kDSt0: return duu[1];
+      case kDThr: return duu[0] - dup[0];
+      case kDSt: return duu[1] - dup[1];
+      case kProg: return dshh - dshp;
+      default: return gC[0] * dxy[0] + gC[1] * dxy[1] + gC[2] * dshh;
+    }
+  }
+
+  // previous-stage quantities via shuffles (lane 0: fixed initial state / wrap)
+  MPCR_D void gather_prev(const double* xx, double shh, const double* uu, double* xp,
+                          double& shp, double* up) const {
+    int src = prev_lane();
+    for (int k = 0; k < 6; ++k) {
+      double t = shfl(xx[k], src);
+      xp[k] = (lane == 0) ? pb.x0[k] : t;
+    }
+    double t = shfl(shh, src);
+    shp = (lane == 0) ? pb.s0 : t;
+    up[0] = shfl(uu[0], src);   // lane 0 receives u_{N-1} (wrap rows)
+    up[1] = shfl(uu[1], src);
+  }
+
+  MPCR_D double barrier_terms(const double* ss) const {
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) {
+      if (!on(r)) continue;
+      double t = 0.0;
+      if (row_hasL(r)) {
+        double sl = ss[r] - lo(r);
+        t -= mu * log(sl);
+        if (!row_hasU(r)) t += o.kappa_d * mu * sl;
+      }
+      if (row_hasU(r)) {
+        double su = hi(r) - ss[r];
+        t -= mu * log(su);
+        if (!row_hasL(r)) t += o.kappa_d * mu * su;
+      }
+      acc += t;
+    }
+    return acc;
+  }
+
+  // -------------------------------------------------------------------------
+  // objective / constraints at a point (line search trial or current iterate)
+  // -------------------------------------------------------------------------
+  struct Point {
+    double x[6], sh, u[2], s[kNumRows];
+    double c[6], rd[kNumRows];
+    double f, theta, phi;   // uniform
+    bool finite;            // uniform
+  };
+
+  MPCR_D void eval_point(Point& t, bool with_slacks) const {
+    double xp[6], shp, up[2];
+    gather_prev(t.x, t.sh, t.u, xp, shp, up);
+    double f[6];
+    f_model(cfg.model, xp, t.u, cfg.Ts, f);
+    StageCost sc;
+    stage_cost(p, pb.cx, pb.cy, t.x, t.sh, 0, sc);
+    double fl = 0.0, th = 0.0;
+    bool fin = true;
+    for (int k = 0; k < 6; ++k) t.c[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) t.rd[r] = 0.0;
+    if (act) {
+      fl = sc.val;
+      if (lane == N - 1) fl -= p.lambda_s * t.sh;
+      if (lane >= 1) {
+        double dsg = t.u[1] - up[1];
+        fl += p.beta_delta * dsg * dsg;
+      }
+      for (int k = 0; k < 6; ++k) {
+        t.c[k] = t.x[k] - f[k];
+        th += fabs(dcs[k] * t.c[k]);
+      }
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        if (!on(r)) continue;
+        double v = row_value(r, t.u, up, t.sh, shp, sc.eC);
+        t.rd[r] = with_slacks ? v - t.s[r] : v;
+        th += fabs(t.rd[r]);
+      }
+      fin = finite_d(fl) && finite_d(th);
+    }
+    t.finite = warp_all(fin);
+    t.f = df * warp_sum(fl);
+    t.theta = warp_sum(th);
+    t.phi = 0.0;
+    if (with_slacks) {
+      double bar = act ? barrier_terms(t.s) : 0.0;
+      t.phi = t.f + warp_sum(bar);
+      if (!finite_d(t.phi)) t.finite = false;
+    }
+  }
+
+  // -------------------------------------------------------------------------
+  // Derivative evaluation at the current iterate; fills the stage storage.
+  // mode 0: Newton step (exact Hessian), mode 1: least-squares multiplier init
+  // -------------------------------------------------------------------------
+  StageLin lin;           // Jacobian blocks of stage `lane`
+  double gcost[5];        // df * grad cost of state lane+1 over (X, Y, s, vx, vy) (incl -lambda_s)
+  double gC[3];           // ddl * grad e_C over (X, Y, s) at state lane+1 (lane row)
+  double sigc_prev;       // sigma_k - sigma_{k-1} (0 for lane 0)
+
+  MPCR_D void eval_derivs(int mode) {
+    double xp[6], shp, up[2];
+    gather_prev(x, sh, u, xp, shp, up);
+    double hm[kHmDoubles];
+    double zero6[6] = {0, 0, 0, 0, 0, 0};
+    lin_model(cfg.model, xp, u, cfg.Ts, mode == 0 ? lam : zero6, nullptr, lin, hm);
+    StageCost sc;
+    stage_cost(p, pb.cx, pb.cy, x, sh, 2, sc);
+    gcost[0] = df * sc.g3[0];
+    gcost[1] = df * sc.g3[1];
+    gcost[2] = df * sc.g3[2] - ((lane == N - 1) ? df * p.lambda_s : 0.0);
+    gcost[3] = df * sc.gvx;
+    gcost[4] = df * sc.gvy;
+    for (int k = 0; k < 3; ++k) gC[k] = ddl * sc.gC[k];
+    sigc_prev = (lane >= 1 && act) ? (u[1] - up[1]) : 0.0;
+    // cost Hessian of state lane+1 -> owner of stage lane+1 (shuffle up) / terminal slot
+    double hc[8];
+    for (int k = 0; k < 8; ++k) hc[k] = 0.0;
+    if (mode == 0 && act) {
+      for (int k = 0; k < 6; ++k) hc[k] = df * sc.h3[k];
+      hc[6] = df * sc.hvx;
+      hc[7] = df * sc.hvy;
+      if (cfg.lane_con && on(kLane)) {
+        double yl = yd[kLane] * ddl;     // + yd * Hess(e_C); the Sigma part is a row term
+        hc[2] += yl * sc.hC02;
+        hc[4] += yl * sc.hC12;
+        hc[5] += yl * sc.hC22;
+      }
+    }
+    double hcp[8];
+    for (int k = 0; k < 8; ++k) {
+      double t = shfl(hc[k], prev_lane());
+      hcp[k] = (lane == 0) ? 0.0 : t;
+    }
+    if (act) {
+      double* st = ws.st(lane);
+      for (int k = 0; k < 3; ++k) { st[kOffA + k] = lin.aX[k]; st[kOffA + 3 + k] = lin.aY[k]; }
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k) st[kOffA + 6 + 3 * i + k] = lin.d[i][k];
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 2; ++k) st[kOffA + 15 + 2 * i + k] = lin.bu[i][k];
+      double* hs = st + kOffHs;
+      for (int k = 0; k < 6; ++k) hs[k] = hcp[k];
+      for (int k = 0; k < kHmDoubles; ++k) hs[6 + k] = (mode == 0) ? -hm[k] : 0.0;
+      hs[6 + hm_idx(1, 1)] += hcp[6];
+      hs[6 + hm_idx(2, 2)] += hcp[7];
+      if (lane == N - 1) {
+        double* hN = ws.st(N) + kOffHs;
+        for (int k = 0; k < 6; ++k) hN[k] = hc[k];
+        for (int k = 0; k < kHmDoubles; ++k) hN[6 + k] = 0.0;
+        hN[6 + hm_idx(1, 1)] = hc[6];
+        hN[6 + hm_idx(2, 2)] = hc[7];
+        for (int k = 27; k < 32; ++k) hN[k] = 0.0;
+        ws.st(N)[kOffRow + 0] = 0.0;
+        ws.st(N)[kOffRow + 1] = 0.0;
+      }
+    }
+  }
+
+  // -------------------------------------------------------------------------
+  // Row-dependent stage terms (depend on Sigma, delta_w and the right-hand side).
+  //   e_r = D_r * rdv_r + gsb_r  is the condensed slack contribution of row r.
+  //   mode 0: Newton/SOC (D = Sigma + dw, gsb = barrier gradient)
+  //   mode 1: LSQ init    (D = 1, gradient = -(grad f + Jd'(vU - vL)))
+  // -------------------------------------------------------------------------
+  double Dw[2];   // D of the two wrap rows (uniform, from lane 0)
+
+  MPCR_D double sigma_row(int r) const {
+    double sg = 0.0;
+    if (row_hasL(r)) sg += vL[r] / (s[r] - lo(r));
+    if (row_hasU(r)) sg += vU[r] / (hi(r) - s[r]);
+    return sg;
+  }
+  MPCR_D double gsb_row(int r) const {   // d(barrier objective)/d(slack r)
+    double g = 0.0;
+    if (row_hasL(r)) {
+      g -= mu / (s[r] - lo(r));
+      if (!row_hasU(r)) g += o.kappa_d * mu;
+    }
+    if (row_hasU(r)) {
+      g += mu / (hi(r) - s[r]);
+      if (!row_hasL(r)) g -= o.kappa_d * mu;
+    }
+    return g;
+  }
+
+  MPCR_D void write_row_terms(int mode, double dw, const double* rdv /* [kNumRows] */,
+                              const double* cv /* [6] dynamics rhs */) {
+    double D[kNumRows], e[kNumRows];
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) {
+      D[r] = 0.0;
+      e[r] = 0.0;
+      if (!on(r) || !act) continue;
+      if (mode == 0) {
+        D[r] = sigma_row(r) + dw;
+        e[r] = D[r] * rdv[r] + gsb_row(r);
+      } else {
+        D[r] = 1.0;
+        e[r] = -((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0));
+      }
+    }
+    const bool wrap0 = (lane == 0);   // rows kDThr/kDSt of lane 0 are the non-local wrap rows
+    double Dw0 = shfl(D[kDThr], 0), Dw1 = shfl(D[kDSt], 0);
+    double ew0 = shfl(e[kDThr], 0), ew1 = shfl(e[kDSt], 0);
+    Dw[0] = Dw0;
+    Dw[1] = Dw1;
+    // cost gradient / lane-row data of state `lane` live in the previous lane
+    double gcp[5], gCp[3];
+    for (int k = 0; k < 5; ++k) {
+      double t = shfl(gcost[k], prev_lane());
+      gcp[k] = (lane == 0) ? 0.0 : t;
+    }
+    double elane_p = shfl(e[kLane], prev_lane()), Dlane_p = shfl(D[kLane], prev_lane());
+    if (lane == 0) { elane_p = 0.0; Dlane_p = 0.0; }
+    for (int k = 0; k < 3; ++k) {
+      double t = shfl(gC[k], prev_lane());
+      gCp[k] = (lane == 0) ? 0.0 : t;
+    }
+    if (!act) return;
+    // steer-rate cost beta (sigma_k - sigma_{k-1})^2, k = 1..N-1 (control/MPC.py:97)
+    const double bsig = (lane >= 1) ? 2.0 * p.beta_delta * df : 0.0;
+    const double sgn = (mode == 0) ? 1.0 : -1.0;   // LSQ uses the negated gradient
+    const double bq = (mode == 0) ? bsig : 0.0;
+    double* st = ws.st(lane);
+    double* hs = st + kOffHs;
+    double* gs = st + kOffGs;
+    const double dthr = wrap0 ? 0.0 : D[kDThr];
+    const double dst = wrap0 ? 0.0 : D[kDSt];
+    hs[27] = D[kProg];
+    hs[28] = dthr;
+    hs[29] = dst + bq;
+    hs[30] = -dthr;
+    hs[31] = -(dst + bq);
+    st[kOffRow + 0] = D[kThrUb] + D[kThrLb] + dthr + D[kDThr0];
+    st[kOffRow + 1] = D[kStUb] + D[kStLb] + dst + bq + D[kDSt0];
+    st[kOffRow + 2] = Dlane_p;
+    st[kOffRow + 3] = gCp[0];
+    st[kOffRow + 4] = gCp[1];
+    st[kOffRow + 5] = gCp[2];
+    double eth = e[kThrUb] + e[kThrLb] + (wrap0 ? 0.0 : e[kDThr]) + e[kDThr0];
+    double est = e[kStUb] + e[kStLb] + (wrap0 ? 0.0 : e[kDSt]) + e[kDSt0];
+    if (cfg.wrap) {
+      if (lane == 0) { eth += ew0; est += ew1; }
+      if (lane == N - 1) { eth -= ew0; est -= ew1; }
+    }
+    const double bg = sgn * bsig * sigc_prev;
+    gs[0] = sgn * gcp[0] + elane_p * gCp[0];
+    gs[1] = sgn * gcp[1] + elane_p * gCp[1];
+    gs[2] = 0.0;
+    gs[3] = sgn * gcp[3];
+    gs[4] = sgn * gcp[4];
+    gs[5] = 0.0;
+    gs[6] = sgn * gcp[2] + elane_p * gCp[2];
+    gs[7] = wrap0 ? 0.0 : -e[kDThr];
+    gs[8] = (wrap0 ? 0.0 : -e[kDSt]) - bg;
+    gs[9] = eth;
+    gs[10] = est + bg;
+    gs[11] = e[kProg];
+    for (int k = 0; k < 6; ++k) st[kOffB + k] = -cv[k];
+    if (lane == N - 1) {
+      double* gN = ws.st(N) + kOffGs;
+      double* lN = ws.st(N) + kOffRow;
+      gN[0] = sgn * gcost[0] + e[kLane] * gC[0];
+      gN[1] = sgn * gcost[1] + e[kLane] * gC[1];
+      gN[2] = 0.0;
+      gN[3] = sgn * gcost[3];
+      gN[4] = sgn * gcost[4];
+      gN[5] = 0.0;
+      gN[6] = sgn * gcost[2] + e[kLane] * gC[2];
+      for (int k = 7; k < 12; ++k) gN[k] = 0.0;
+      lN[2] = D[kLane];
+      lN[3] = gC[0];
+      lN[4] = gC[1];
+      lN[5] = gC[2];
+    }
+  }
+
+  // value of the assembled stage Hessian at a packed slot (+ regularisation flag)
+  MPCR_D double stage_entry(const double* st, int slot, double dw) const {
+    const int sl = slot & 0xff;
+    double v = 0.0;
+    if (sl != 0xff) {
+      v = st[kOffHs + sl];
+      if (sl == 6 + hm_idx(4, 4)) v += st[kOffRow + 0];
+      if (sl == 6 + hm_idx(5, 5)) v += st[kOffRow + 1];
+      if (sl < 6) {          // lane-row Sigma term on (X, Y, s)
+        const double Dl = st[kOffRow + 2];
+        if (Dl != 0.0) {
+          const int ia = (sl < 3) ? 0 : ((sl < 5) ? 1 : 2);
+          const int ib = (sl < 3) ? sl : ((sl < 5) ? sl - 2 : 2);
+          v += Dl * st[kOffRow + 3 + ia] * st[kOffRow + 3 + ib];
+        }
+      }
+    }
+    if (slot & 0x100) v += dw;
+    return v;
+  }
+  MPCR_D int slot_of(int r, int c) const {
+    int sl = hs_slot(r, c);
+    int slot = (sl < 0) ? 0xff : sl;
+    if (r == c && (r <= 6 || r == 9 || r == 10)) slot |= 0x100;
+    return slot;
+  }
+
+  // -------------------------------------------------------------------------
+  // Riccati factorisation + solve for 3 right-hand sides.
+  //   rhs 0: the Newton (or LSQ / SOC) right-hand side stored in the stages
+  //   rhs 1, 2: the wrap vectors a_1 = e(thr_0) - e(thr_{N-1}), a_2 (steer)
+  // Returns false when a pivot block is not positive definite (wrong inertia).
+  // -------------------------------------------------------------------------
+  double mz[kRhs][7];   // (dx_{k+1} (6), ds_{k+1}) for the 3 right-hand sides
+  double mw[kRhs][2];   // (dthr_k, dst_k)
+
+  MPCR_D bool riccati(double dw) {
+    const double Ts = cfg.Ts;
+    double* P = ws.P;
+    double* T = ws.T;
+    double* G = ws.G;
+    const int nrhs = cfg.wrap ? kRhs : 1;
+    {
+      const double* stN = ws.st(N);
+      for (int j = 0; j < 3; ++j) {
+        int e = lane + 32 * j;
+        if (e < 81) {
+          int r = e / 9, c = e % 9;
+          P[e] = stage_entry(stN, slot_of(r, c), dw);
+        }
+      }
+      if (lane < 27) {
+        int j = lane / 9, a = lane % 9;
+        ws.pv[lane] = (j == 0) ? stN[kOffGs + a] : 0.0;
+      }
+    }
+    syncwarp();
+    bool ok = true;
+    for (int k = N - 1; k >= 0; --k) {
+      double* st = ws.st(k);
+      // ---- round 1: T = P M (rows), t_j = p_j + P b_j ; G <- stage Hessian ----
+      if (lane < 9) {
+        double pr[9], A[21], out[12];
+        for (int c = 0; c < 9; ++c) pr[c] = P[lane * 9 + c];
+        for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
+        mulM(pr, A, Ts, out);
+        for (int c = 0; c < 12; ++c) T[lane * 12 + c] = out[c];
+        double t0 = ws.pv[lane];
+        for (int c = 0; c < 6; ++c) t0 += pr[c] * st[kOffB + c];
+        ws.tv[lane] = t0;
+        ws.tv[9 + lane] = ws.pv[9 + lane];
+        ws.tv[18 + lane] = ws.pv[18 + lane];
+      }
+      for (int j = 0; j < 5; ++j) {
+        int e = lane + 32 * j;
+        if (e < 144) G[e] = stage_entry(st, gslot[j], dw);
+      }
+      syncwarp();
+      // ---- round 2: G[:, c] += M' T[:, c] ; g_j = grad_j + M' t_j -----------------
+      if (lane < 12) {
+        if (lane != 7 && lane != 8) {
+          double tc[9], A[21], out[12];
+          for (int r = 0; r < 9; ++r) tc[r] = T[r * 12 + lane];
+          for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
+          mulM(tc, A, Ts, out);
+          for (int r = 0; r < 12; ++r) G[r * 12 + lane] += out[r];
+        }
+      } else if (lane < 12 + nrhs) {
+        const int j = lane - 12;
+        double tc[9], A[21], out[12];
+        for (int r = 0; r < 9; ++r) tc[r] = ws.tv[j * 9 + r];
+        for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
+        mulM(tc, A, Ts, out);
+        for (int r = 0; r < 12; ++r) {
+          double g = out[r];
+          if (j == 0) g += st[kOffGs + r];
+          ws.gv[j * 12 + r] = g;
+        }
+        if (j >= 1) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
+          double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
+          ws.gv[j * 12 + 9 + (j - 1)] += a;
+        }
+      }
+      syncwarp();
+      // ---- round 3: LDL' of H_ww (every lane), gains, cost-to-go update ------------
+      const double h00 = G[9 * 12 + 9], h10 = G[10 * 12 + 9], h20 = G[11 * 12 + 9];
+      const double h11 = G[10 * 12 + 10], h21 = G[11 * 12 + 10], h22 = G[11 * 12 + 11];
+      const double d0 = h00;
+      const double id0 = 1.0 / d0;
+      const double l10 = h10 * id0, l20 = h20 * id0;
+      const double d1 = h11 - l10 * h10;
+      const double id1 = 1.0 / d1;
+      const double m21 = h21 - l20 * h10;
+      const double l21 = m21 * id1;
+      const double d2 = h22 - l20 * h20 - l21 * m21;
+      const double id2 = 1.0 / d2;
+      // identical in every lane (same inputs, same arithmetic) -> uniform branch
+      if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) { ok = false; break; }
+      if (lane < 9 || (lane >= 12 && lane < 12 + nrhs)) {
+        double r0, r1, r2;
+        const int c = lane;
+        const int j = lane - 12;
+        if (lane < 9) {
+          r0 = G[9 * 12 + c]; r1 = G[10 * 12 + c]; r2 = G[11 * 12 + c];
+        } else {
+          r0 = ws.gv[j * 12 + 9]; r1 = ws.gv[j * 12 + 10]; r2 = ws.gv[j * 12 + 11];
+        }
+        const double f0 = r0, f1 = r1 - l10 * f0, f2 = r2 - l20 * f0 - l21 * f1;
+        const double z2 = f2 * id2;
+        const double z1 = f1 * id1 - l21 * z2;
+        const double z0 = f0 * id0 - l10 * z1 - l20 * z2;
+        const double k0 = -z0, k1 = -z1, k2 = -z2;
+        if (lane < 9) {
+          st[kOffK + 0 * 9 + c] = k0;
+          st[kOffK + 1 * 9 + c] = k1;
+          st[kOffK + 2 * 9 + c] = k2;
+          for (int a = 0; a < 9; ++a)
+            P[a * 9 + c] = G[a * 12 + c] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
+                           G[11 * 12 + a] * k2;
+        } else {
+          st[kOffKf + j * 3 + 0] = k0;
+          st[kOffKf + j * 3 + 1] = k1;
+          st[kOffKf + j * 3 + 2] = k2;
+          for (int a = 0; a < 9; ++a)
+            ws.pv[j * 9 + a] = ws.gv[j * 12 + a] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
+                               G[11 * 12 + a] * k2;
+        }
+      }
+      syncwarp();
+    }
+    if (!ok) return false;
+    // ---- forward sweep (replicated in every lane; lane k keeps stage k) -----------
+    double z[kRhs][9];
+    for (int j = 0; j < kRhs; ++j) {
+      for (int a = 0; a < 9; ++a) z[j][a] = 0.0;
+      for (int a = 0; a < 7; ++a) mz[j][a] = 0.0;
+      mw[j][0] = mw[j][1] = 0.0;
+    }
+    for (int k = 0; k < N; ++k) {
+      const double* st = ws.st(k);
+      double A[21];
+      for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
+      for (int j = 0; j < nrhs; ++j) {
+        double w[3];
+        for (int i = 0; i < 3; ++i) {
+          double acc = st[kOffKf + j * 3 + i];
+          for (int a = 0; a < 9; ++a) acc += st[kOffK + i * 9 + a] * z[j][a];
+          w[i] = acc;
+        }
+        double zn[9];
+        applyM(z[j], w, A, Ts, zn);
+        if (j == 0)
+          for (int a = 0; a < 6; ++a) zn[a] += st[kOffB + a];
+        for (int a = 0; a < 9; ++a) z[j][a] = zn[a];
+        if (k == lane) {
+          for (int a = 0; a < 7; ++a) mz[j][a] = zn[a];
+          mw[j][0] = w[0];
+          mw[j][1] = w[1];
+        }
+      }
+    }
+    return true;
+  }
+
+  // -------------------------------------------------------------------------
+  // Full KKT solve: Riccati + Woodbury combination + costate recursion.
+  // Outputs dx, dsh, du (primal step) and newlam / newy0 = the NEW equality
+  // multipliers (y + dy) of the linearised problem.
+  // -------------------------------------------------------------------------
+  double newlam[6], newy0[7];
+
+  MPCR_D bool kkt_solve(double dw) {
+    if (!riccati(dw)) return false;
+    // Woodbury: x = x0 + sum_k D_k t_k X_k with (I - M D) t = t0, M_ik = a_i' X_k
+    double c1 = 0.0, c2 = 0.0;
+    if (cfg.wrap) {
+      double t0[2], Mm[2][2];
+      for (int i = 0; i < 2; ++i) {
+        t0[i] = shfl(mw[0][i], 0) - shfl(mw[0][i], N - 1);
+        for (int kk = 0; kk < 2; ++kk)
+          Mm[i][kk] = shfl(mw[1 + kk][i], 0) - shfl(mw[1 + kk][i], N - 1);
+      }
+      const double a00 = 1.0 - Mm[0][0] * Dw[0], a01 = -Mm[0][1] * Dw[1];
+      const double a10 = -Mm[1][0] * Dw[0], a11 = 1.0 - Mm[1][1] * Dw[1];
+      const double det = a00 * a11 - a01 * a10;
+      const double t1 = (a11 * t0[0] - a01 * t0[1]) / det;
+      const double t2 = (-a10 * t0[0] + a00 * t0[1]) / det;
+      c1 = Dw[0] * t1;
+      c2 = Dw[1] * t2;
+    }
+    for (int a = 0; a < 6; ++a) dx[a] = mz[0][a] + c1 * mz[1][a] + c2 * mz[2][a];
+    dsh = mz[0][6] + c1 * mz[1][6] + c2 * mz[2][6];
+    for (int i = 0; i < 2; ++i) du[i] = mw[0][i] + c1 * mw[1][i] + c2 * mw[2][i];
+    // costates: pi_j = local_j + A_j' pi_{j+1}, local_j = Q_j dz_j + S_j' dw_j + q_j
+    double dzp[7];
+    for (int a = 0; a < 6; ++a) {
+      double t = shfl(dx[a], prev_lane());
+      dzp[a] = (lane == 0) ? 0.0 : t;
+    }
+    {
+      double t = shfl(dsh, prev_lane());
+      dzp[6] = (lane == 0) ? 0.0 : t;
+    }
+    double* loc = ws.T;   // scratch [(N+1)][7]: T (108) + G (144) are contiguous
+    if (act) {
+      const double* st = ws.st(lane);
+      const double v12[12] = {dzp[0], dzp[1], dzp[2], dzp[3], dzp[4], dzp[5], dzp[6], 0, 0,
+                              du[0], du[1], 0};
+      for (int a = 0; a < 7; ++a) {
+        double acc = st[kOffGs + a];
+        for (int c = 0; c < 11; ++c) {
+          if (c == 7 || c == 8) continue;
+          const int slot = slot_of(a, c);
+          if (slot == 0xff) continue;
+          acc += stage_entry(st, slot, dw) * v12[c];
+        }
+        loc[lane * 7 + a] = acc;
+      }
+      if (lane == N - 1) {
+        const double* sN = ws.st(N);
+        const double vN[7] = {dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dsh};
+        for (int a = 0; a < 7; ++a) {
+          double acc = sN[kOffGs + a];
+          for (int c = 0; c < 7; ++c) {
+            const int slot = slot_of(a, c);
+            if (slot == 0xff) continue;
+            acc += stage_entry(sN, slot, dw) * vN[c];
+          }
+          loc[N * 7 + a] = acc;
+        }
+      }
+    }
+    syncwarp();
+    double pi[7];
+    for (int a = 0; a < 7; ++a) pi[a] = loc[N * 7 + a];
+    for (int a = 0; a < 6; ++a) newlam[a] = 0.0;
+    if (lane == N - 1)
+      for (int a = 0; a < 6; ++a) newlam[a] = -pi[a];
+    for (int j = N - 1; j >= 0; --j) {
+      const double* st = ws.st(j);
+      const double *aX = st + kOffA, *aY = st + kOffA + 3, *d = st + kOffA + 6;
+      double q[7];
+      q[0] = pi[0];
+      q[1] = pi[1];
+      q[2] = aX[0] * pi[0] + aY[0] * pi[1] + pi[2];
+      q[3] = aX[1] * pi[0] + aY[1] * pi[1] + d[0] * pi[3] + d[3] * pi[4] + d[6] * pi[5];
+      q[4] = aX[2] * pi[0] + aY[2] * pi[1] + d[1] * pi[3] + d[4] * pi[4] + d[7] * pi[5];
+      q[5] = cfg.Ts * pi[2] + d[2] * pi[3] + d[5] * pi[4] + d[8] * pi[5];
+      q[6] = pi[6];
+      for (int a = 0; a < 7; ++a) pi[a] = loc[j * 7 + a] + q[a];
+      if (j == lane + 1)
+        for (int a = 0; a < 6; ++a) newlam[a] = -pi[a];
+    }
+    for (int a = 0; a < 7; ++a) newy0[a] = -pi[a];
+    syncwarp();
+    return true;
+  }
+
+  // -------------------------------------------------------------------------
+  // Optimality error E_mu (Waechter & Biegler eq. (5)) and its ingredients
+  // -------------------------------------------------------------------------
+  struct Errors { double E, dual_inf, pr_inf, compl_inf; };
+  int n_eq_ineq, n_bounds;   // uniform counts: rows with multipliers, bound multipliers
+
+  MPCR_D Errors compute_errors(double mu_t) const {
+    // t = A' lam: contributions of this stage's dynamics rows to (x_k, u_k)
+    double A[21], lv[9], out[12];
+    for (int k = 0; k < 3; ++k) { A[k] = lin.aX[k]; A[3 + k] = lin.aY[k]; }
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) A[6 + 3 * i + k] = lin.d[i][k];
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 2; ++k) A[15 + 2 * i + k] = lin.bu[i][k];
+    for (int k = 0; k < 6; ++k) lv[k] = act ? lam[k] : 0.0;
+    lv[6] = lv[7] = lv[8] = 0.0;
+    mulM(lv, A, cfg.Ts, out);
+    const bool last = (lane == N - 1);
+    double dinf = 0.0;
+    // x_{k+1}
+    double txn[6];
+    for (int a = 0; a < 6; ++a) {
+      double t = shfl(out[a], next_lane());
+      txn[a] = last ? 0.0 : t;
+    }
+    const double ydl = on(kLane) ? yd[kLane] : 0.0;
+    const double gx[6] = {gcost[0] + ydl * gC[0], gcost[1] + ydl * gC[1], 0.0, gcost[3],
+                          gcost[4], 0.0};
+    const double yprog_n_raw = shfl(yd[kProg], next_lane());
+    const double yprog_n = last ? 0.0 : yprog_n_raw;
+    const double ydthr_n = shfl(on(kDThr) ? yd[kDThr] : 0.0, next_lane());
+    const double ydst_n = shfl(on(kDSt) ? yd[kDSt] : 0.0, next_lane());
+    const double sig_n_raw = shfl(sigc_prev, next_lane());
+    const double sig_n = last ? 0.0 : sig_n_raw;
+    double prinf = 0.0, cmpl = 0.0, sum_y = 0.0, sum_v = 0.0;
+    if (act) {
+      for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(gx[a] + lam[a] - txn[a]));
+      dinf = fmax(dinf, fabs(gcost[2] + ydl * gC[2] + yd[kProg] - yprog_n));
+      double ru0 = -out[9] + yd[kThrUb] + yd[kThrLb] + (on(kDThr) ? yd[kDThr] : 0.0) - ydthr_n +
+                   (on(kDThr0) ? yd[kDThr0] : 0.0);
+      double ru1 = -out[10] + yd[kStUb] + yd[kStLb] + (on(kDSt) ? yd[kDSt] : 0.0) - ydst_n +
+                   (on(kDSt0) ? yd[kDSt0] : 0.0) +
+                   2.0 * p.beta_delta * df * (sigc_prev - sig_n);
+      dinf = fmax(dinf, fmax(fabs(ru0), fabs(ru1)));
+      if (lane == 0) {
+        for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(y0[a] - out[a]));
+        dinf = fmax(dinf, fabs(y0[6] - yd[kProg]));
+        for (int a = 0; a < 7; ++a) sum_y += fabs(y0[a]);
+      }
+      for (int a = 0; a < 6; ++a) {
+        prinf = fmax(prinf, fabs(dcs[a] * cres[a]));
+        sum_y += fabs(lam[a] / dcs[a]);
+      }
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        if (!on(r)) continue;
+        double rs = -yd[r];
+        if (row_hasL(r)) {
+          rs -= vL[r];
+          cmpl = fmax(cmpl, fabs((s[r] - lo(r)) * vL[r] - mu_t));
+          sum_v += fabs(vL[r]);
+        }
+        if (row_hasU(r)) {
+          rs += vU[r];
+          cmpl = fmax(cmpl, fabs((hi(r) - s[r]) * vU[r] - mu_t));
+          sum_v += fabs(vU[r]);
+        }
+        dinf = fmax(dinf, fabs(rs));
+        prinf = fmax(prinf, fabs(rd[r]));
+        sum_y += fabs(yd[r]);
+      }
+    }
+    Errors e;
+    e.dual_inf = warp_max(dinf);
+    e.pr_inf = warp_max(prinf);
+    e.compl_inf = warp_max(cmpl);
+    sum_y = warp_sum(sum_y);
+    sum_v = warp_sum(sum_v);
+    const double smax = o.s_max;
+    const double s_d = fmax(smax, (sum_y + sum_v) / (double)(n_eq_ineq + n_bounds)) / smax;
+    const double s_c = fmax(smax, sum_v / (double)n_bounds) / smax;
+    e.E = fmax(e.dual_inf / s_d, fmax(e.pr_inf, e.compl_inf / s_c));
+    return e;
+  }
+
+  // max violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
+  MPCR_D double orig_violation() const {
+    double v = 0.0;
+    if (act) {
+      for (int a = 0; a < 6; ++a) v = fmax(v, fabs(cres[a]));
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        if (!on(r)) continue;
+        double l, h;
+        row_bounds(r, l, h);
+        double val = rd[r] + s[r];
+        if (r == kLane) val /= ddl;
+        if (row_hasL(r)) v = fmax(v, l - val);
+        if (row_hasU(r)) v = fmax(v, val - h);
+      }
+    }
+    return warp_max(v);
+  }
+
+  MPCR_D double theta_local() const {
+    double th = 0.0;
+    if (act) {
+      for (int a = 0; a < 6; ++a) th += fabs(dcs[a] * cres[a]);
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r)
+        if (on(r)) th += fabs(rd[r]);
+    }
+    return th;
+  }
+
+  // filter --------------------------------------------------------------------
+  MPCR_D bool filter_ok(double th, double ph) const {
+    int n = filt_n < 32 ? filt_n : 32;
+    bool ok = (lane >= n) || (th <= filt_th) || (ph <= filt_ph);
+    return warp_all(ok);
+  }
+  MPCR_D void filter_add(double th, double ph) {
+    if (lane == (filt_n & 31)) { filt_th = th; filt_ph = ph; }
+    filt_n++;
+  }
+  MPCR_D static bool cmp_le(double a, double b, double ref) {
+    return a - b <= 10.0 * 2.220446049250313e-16 * fabs(ref);
+  }
+
+  // fraction-to-the-boundary step for the slacks given ds (per row), and for v
+  MPCR_D double ftb_primal(const double* dsr) const {
+    double a = 1.0;
+    if (act) {
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        if (!on(r)) continue;
+        if (row_hasL(r) && dsr[r] < 0.0) a = fmin(a, -tau * (s[r] - lo(r)) / dsr[r]);
+        if (row_hasU(r) && dsr[r] > 0.0) a = fmin(a, tau * (hi(r) - s[r]) / dsr[r]);
+      }
+    }
+    return warp_min(a);
+  }
+
+  MPCR_D void slack_steps(const double* rdv, double* dsr) const {
+    // ds_r = J_r dx + rdv_r
+    double dup[2], dshp;
+    dup[0] = shfl(du[0], prev_lane());
+    dup[1] = shfl(du[1], prev_lane());
+    double t = shfl(dsh, prev_lane());
+    dshp = (lane == 0) ? 0.0 : t;
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) {
+      dsr[r] = 0.0;
+      if (!on(r) || !act) continue;
+      dsr[r] = row_lin(r, du, dup, dsh, dshp, dx) + rdv[r];
+    }
+  }
+
+  // -------------------------------------------------------------------------
+  MPCR_D void solve(const SolveOut& out) {
+    const double inf = 1.0e300;
+    // ---- rows ---------------------------------------------------------------
+    rowmask = 0;
+    if (act) {
+      rowmask = 0x4F;                                  // rows 0-3, 6
+      if (lane > 0 || cfg.wrap) rowmask |= (1u << kDThr) | (1u << kDSt);
+      if (lane == 0 && pb.has_prev_thr) rowmask |= 1u << kDThr0;
+      if (lane == 0 && pb.has_prev_st) rowmask |= 1u << kDSt0;
+      if (cfg.lane_con) rowmask |= 1u << kLane;
+    }
+    // ---- initial guess (control/MPC.py:109-131) ----------------------------------
+    {
+      double u0 = pb.u_prev[0], u1 = pb.u_prev[1];
+      if (pb.u_warm && act) {
+        int src = (lane + 1 < N) ? lane + 1 : N - 1;   // shift by one, repeat the last
+        u0 = pb.u_warm[src];
+        u1 = pb.u_warm[N + src];
+      }
+      u[0] = act ? u0 : 0.0;
+      u[1] = act ? u1 : 0.0;
+      double xr[6];
+      for (int k = 0; k < 6; ++k) { xr[k] = pb.x0[k]; x[k] = pb.x0[k]; }
+      for (int k = 0; k < N; ++k) {
+        double uk[2] = {shfl(u[0], k), shfl(u[1], k)};
+        double fn[6];
+        f_dynamic(xr, uk, cfg.Ts, fn);                 // always f_vehicle (MPC.py:129)
+        for (int a = 0; a < 6; ++a) xr[a] = fn[a];
+        if (k == lane)
+          for (int a = 0; a < 6; ++a) x[a] = fn[a];
+      }
+      sh = act ? pb.s0 + (lane + 1) * cfg.Ts * p.v_max : pb.s0;
+    }
+    for (int k = 0; k < 6; ++k) { lam[k] = 0.0; dcs[k] = 1.0; cres[k] = 0.0; }
+    for (int k = 0; k < 7; ++k) y0[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) { s[r] = 0.0; yd[r] = 0.0; vL[r] = 0.0; vU[r] = 0.0; rd[r] = 0.0; }
+    df = 1.0;
+    ddl = 1.0;
+    mu = o.mu_init;
+    tau = fmax(o.tau_min, 1.0 - mu);
+    filt_n = 0;
+    filt_th = 0.0;
+    filt_ph = 0.0;
+    // counts
+    {
+      int nr = 0, nb = 0;
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r)
+        if (on(r)) { nr += 1; nb += (row_hasL(r) ? 1 : 0) + (row_hasU(r) ? 1 : 0); }
+      n_eq_ineq = (int)(warp_sum((double)nr) + 0.5) + 6 * N + 7;
+      n_bounds = (int)(warp_sum((double)nb) + 0.5);
+    }
+    // ---- gradient-based scaling at the starting point -------------------------------
+    eval_derivs(1);
+    {
+      double sig_n_raw = shfl(sigc_prev, next_lane());
+      double sig_n = (lane == N - 1) ? 0.0 : sig_n_raw;
+      double g = 0.0;
+      if (act) {
+        for (int k = 0; k < 5; ++k) g = fmax(g, fabs(gcost[k]));
+        g = fmax(g, fabs(2.0 * p.beta_delta * (sigc_prev - sig_n)));
+      }
+      g = warp_max(g);
+      if (g > o.nlp_scaling_max_gradient)
+        df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
+      double rm[6];
+      rm[0] = fmax(1.0, fmax(fabs(lin.aX[0]), fmax(fabs(lin.aX[1]), fabs(lin.aX[2]))));
+      rm[1] = fmax(1.0, fmax(fabs(lin.aY[0]), fmax(fabs(lin.aY[1]), fabs(lin.aY[2]))));
+      rm[2] = fmax(1.0, fabs(cfg.Ts));
+      for (int i = 0; i < 3; ++i) {
+        double m = 1.0;
+        for (int k = 0; k < 3; ++k) m = fmax(m, fabs(lin.d[i][k]));
+        for (int k = 0; k < 2; ++k) m = fmax(m, fabs(lin.bu[i][k]));
+        rm[3 + i] = m;
+      }
+      for (int k = 0; k < 6; ++k)
+        dcs[k] = (rm[k] > o.nlp_scaling_max_gradient)
+                     ? fmax(o.nlp_scaling_max_gradient / rm[k], o.nlp_scaling_min_value) : 1.0;
+      double gl = fmax(fabs(gC[0]), fmax(fabs(gC[1]), fabs(gC[2])));
+      if (cfg.lane_con && gl > o.nlp_scaling_max_gradient)
+        ddl = fmax(o.nlp_scaling_max_gradient / gl, o.nlp_scaling_min_value);
+    }
+    // ---- relaxed bounds (uniform rows in shared; the lane row scales per lane -> ddl
+    //      is made uniform by using the warp minimum) ------------------------------------
+    ddl = warp_min(act ? ddl : 1.0);
+    if (lane < kNumRows) {
+      double l, h;
+      row_bounds(lane, l, h);
+      if (lane == kLane) { l *= ddl; h *= ddl; }
+      if (row_hasL(lane)) l -= fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(l)));
+      else l = -inf;
+      if (row_hasU(lane)) h += fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(h)));
+      else h = inf;
+      ws.misc[lane] = l;
+      ws.misc[kNumRows + lane] = h;
+    }
+    syncwarp();
+    // ---- slacks pushed into their bounds ---------------------------------------------
+    Point cur;
+    for (int k = 0; k < 6; ++k) cur.x[k] = x[k];
+    cur.sh = sh;
+    cur.u[0] = u[0];
+    cur.u[1] = u[1];
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) cur.s[r] = 0.0;
+    eval_point(cur, false);
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) {
+      if (!on(r)) { s[r] = 0.0; continue; }
+      double v = cur.rd[r];
+      const double l = lo(r), h = hi(r);
+      double pl, pu;
+      if (row_hasL(r) && row_hasU(r)) {
+        pl = fmin(o.bound_push * fmax(1.0, fabs(l)), o.bound_frac * (h - l));
+        pu = fmin(o.bound_push * fmax(1.0, fabs(h)), o.bound_frac * (h - l));
+      } else {
+        pl = o.bound_push * fmax(1.0, fabs(l));
+        pu = o.bound_push * fmax(1.0, fabs(h));
+      }
+      if (row_hasL(r)) v = fmax(v, l + pl);
+      if (row_hasU(r)) v = fmin(v, h - pu);
+      s[r] = v;
+      vL[r] = row_hasL(r) ? o.bound_mult_init_val : 0.0;
+      vU[r] = row_hasU(r) ? o.bound_mult_init_val : 0.0;
+    }
+    // ---- least-squares equality multipliers -----------------------------------------
+    eval_derivs(1);
+    {
+      double zr[kNumRows], zc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) zr[r] = 0.0;
+      write_row_terms(1, 1.0, zr, zc);
+      syncwarp();
+      bool ok = kkt_solve(1.0);
+      double dsr[kNumRows];
+      slack_steps(zr, dsr);     // J_d dx
+      double ymax = 0.0;
+      if (ok && act) {
+        for (int a = 0; a < 6; ++a) { lam[a] = -newlam[a]; ymax = fmax(ymax, fabs(lam[a] / dcs[a])); }
+#pragma unroll
+        for (int r = 0; r < kNumRows; ++r) {
+          if (!on(r)) continue;
+          yd[r] = ((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0)) - dsr[r];
+          ymax = fmax(ymax, fabs(yd[r]));
+        }
+      }
+      for (int a = 0; a < 7; ++a) { y0[a] = ok ? -newy0[a] : 0.0; ymax = fmax(ymax, fabs(y0[a])); }
+      ymax = warp_max(ymax);
+      if (!ok || !(ymax <= o.constr_mult_init_max)) {
+        for (int a = 0; a < 6; ++a) lam[a] = 0.0;
+        for (int a = 0; a < 7; ++a) y0[a] = 0.0;
+#pragma unroll
+        for (int r = 0; r < kNumRows; ++r) yd[r] = 0.0;
+      }
+    }
+    // ---- current point -----------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) cur.s[r] = s[r];
+    eval_point(cur, true);
+    for (int k = 0; k < 6; ++k) cres[k] = cur.c[k];
+#pragma unroll
+    for (int r = 0; r < kNumRows; ++r) rd[r] = cur.rd[r];
+    fval = cur.f;
+    bool cur_finite = cur.finite;
+    const double theta0 = cur.theta;
+    const double theta_max = o.theta_max_fact * fmax(1.0, theta0);
+    const double theta_min = o.theta_min_fact * fmax(1.0, theta0);
+    double dw_last = 0.0;
+    int acc_count = 0;
+    int status = kMaxIterExceeded;
+    int it = 0;
+    const double mu_floor =
+        fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol * df) / (o.barrier_tol_factor + 1.0));
+    double last_alpha = 0.0, last_dw = 0.0;
+
+    while (true) {
+      eval_derivs(0);
+      if (!cur_finite) { status = kInvalidNumber; break; }
+      // ---- convergence tests -----------------------------------------------------------
+      Errors e0 = compute_errors(0.0);
+      const double viol = orig_violation();
+      if (out.trace && lane == 0) {
+        double* tr = out.trace + (size_t)it * kTraceCols;
+        tr[0] = fval / df; tr[1] = e0.E; tr[2] = e0.pr_inf; tr[3] = e0.dual_inf;
+        tr[4] = e0.compl_inf; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
+      }
+      if (!finite_d(e0.E)) { status = kInvalidNumber; break; }
+      if (e0.E <= o.tol && e0.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
+          e0.compl_inf / df <= o.compl_inf_tol) {
+        status = kSolveSucceeded;
+        break;
+      }
+      if (e0.E <= o.acceptable_tol && e0.dual_inf / df <= o.acceptable_dual_inf_tol &&
+          viol <= o.acceptable_constr_viol_tol &&
+          e0.compl_inf / df <= o.acceptable_compl_inf_tol) {
+        acc_count++;
+        if (acc_count >= o.acceptable_iter) { status = kSolvedToAcceptableLevel; break; }
+      } else {
+        acc_count = 0;
+      }
+      if (it >= o.max_iter) { status = kMaxIterExceeded; break; }
+      // ---- barrier parameter update (monotone) ---------------------------------------
+      while (true) {
+        Errors em = compute_errors(mu);
+        if (em.E <= o.barrier_tol_factor * mu && mu > mu_floor) {
+          mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
+                                   pow(mu, o.mu_superlinear_decrease_power)));
+          tau = fmax(o.tau_min, 1.0 - mu);
+          filt_n = 0;
+        } else {
+          break;
+        }
+      }
+      // ---- search direction with inertia correction ----------------------------------
+      double dw = 0.0;
+      bool first_try = true, failed = false;
+      while (true) {
+        write_row_terms(0, dw, rd, cres);
+        syncwarp();
+        if (kkt_solve(dw)) break;
+        if (first_try) {
+          dw = (dw_last == 0.0) ? o.delta_w_init : fmax(o.delta_w_min, dw_last * o.kappa_w_minus);
+          first_try = false;
+        } else {
+          dw *= (dw_last == 0.0 || 1.0e5 * dw_last < dw) ? o.kappa_w_plus_first : o.kappa_w_plus;
+        }
+        if (dw > o.delta_w_max) { failed = true; break; }
+      }
+      if (failed) { status = kErrorInStepComputation; break; }
+      if (dw > 0.0) dw_last = dw;
+      last_dw = dw;
+      // ---- slack / multiplier steps ---------------------------------------------------
+      double dsr[kNumRows];
+      slack_steps(rd, dsr);
+      double alpha_max = ftb_primal(dsr);
+      // grad(phi)' d
+      double gpd = 0.0;
+      {
+        const double dup1 = shfl(du[1], prev_lane());
+        if (act) {
+          gpd = gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
+                gcost[4] * dx[4];
+          // steer-rate cost: 2 beta df (sig_k - sig_{k-1}) (dsig_k - dsig_{k-1})
+          if (lane >= 1) gpd += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
+#pragma unroll
+          for (int r = 0; r < kNumRows; ++r)
+            if (on(r)) gpd += gsb_row(r) * dsr[r];
+        }
+      }
+      gpd = warp_sum(gpd);
+      const double theta = warp_sum(theta_local());
+      const double phi = fval + warp_sum(act ? barrier_terms(s) : 0.0);
+      double amin;
+      if (gpd < 0.0) {
+        amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
+        if (theta <= theta_min)
+          amin = fmin(amin, o.delta * pow(theta, o.s_theta) / pow(-gpd, o.s_phi));
+      } else {
+        amin = o.gamma_theta;
+      }
+      amin *= o.alpha_min_frac;
+      // ---- filter line search ------------------------------------------------------------
+      double alpha = alpha_max;
+      bool accepted = false, f_type = false, soc_done = false;
+      int n_ls = 0;
+      Point tp;
+      double acc_newlam[6], acc_newy0[7];
+      for (int a = 0; a < 6; ++a) acc_newlam[a] = newlam[a];
+      for (int a = 0; a < 7; ++a) acc_newy0[a] = newy0[a];
+      double acc_dsr[kNumRows];
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) acc_dsr[r] = dsr[r];
+      const bool sw_base = gpd < 0.0;
+      while ((alpha >= amin || n_ls == 0) && n_ls < 60) {
+        for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + alpha * dx[a];
+        tp.sh = sh + alpha * dsh;
+        tp.u[0] = u[0] + alpha * du[0];
+        tp.u[1] = u[1] + alpha * du[1];
+#pragma unroll
+        for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + alpha * dsr[r];
+        eval_point(tp, true);
+        n_ls++;
+        bool ok = tp.finite && tp.theta <= theta_max;
+        if (ok) {
+          const bool switching =
+              sw_base && alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
+          if (theta <= theta_min && switching) {
+            ok = cmp_le(tp.phi - phi, o.eta_phi * alpha * gpd, phi);
+            f_type = true;
+          } else {
+            ok = cmp_le(tp.theta, (1.0 - o.gamma_theta) * theta, theta) ||
+                 cmp_le(tp.phi - phi, -o.gamma_phi * theta, phi);
+            f_type = false;
+          }
+          if (ok) ok = filter_ok(tp.theta, tp.phi);
+        }
+        if (ok) { accepted = true; break; }
+        // ---- second-order correction on the first trial step ---------------------------
+        if (!soc_done && n_ls == 1 && tp.finite && tp.theta >= theta) {
+          soc_done = true;
+          double c_soc[6], d_soc[kNumRows];
+          for (int a = 0; a < 6; ++a) c_soc[a] = alpha * cres[a] + tp.c[a];
+#pragma unroll
+          for (int r = 0; r < kNumRows; ++r) d_soc[r] = alpha * rd[r] + tp.rd[r];
+          double th_old = theta;
+          // keep the plain step to restore if no SOC step is accepted
+          double dx0[6], dsh0 = dsh, du0[2] = {du[0], du[1]};
+          for (int a = 0; a < 6; ++a) dx0[a] = dx[a];
+          for (int isoc = 0; isoc < o.max_soc; ++isoc) {
+            write_row_terms(0, dw, d_soc, c_soc);
+            syncwarp();
+            if (!kkt_solve(dw)) break;
+            double dss[kNumRows];
+            slack_steps(d_soc, dss);
+            const double a_soc = ftb_primal(dss);
+            for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + a_soc * dx[a];
+            tp.sh = sh + a_soc * dsh;
+            tp.u[0] = u[0] + a_soc * du[0];
+            tp.u[1] = u[1] + a_soc * du[1];
+#pragma unroll
+            for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + a_soc * dss[r];
+            eval_point(tp, true);
+            if (!tp.finite || tp.theta > theta_max) break;
+            const bool switching =
+                sw_base && alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
+            bool ok2;
+            if (theta <= theta_min && switching) {
+              ok2 = cmp_le(tp.phi - phi, o.eta_phi * alpha * gpd, phi);
+              f_type = true;
+            } else {
+              ok2 = cmp_le(tp.theta, (1.0 - o.gamma_theta) * theta, theta) ||
+                    cmp_le(tp.phi - phi, -o.gamma_phi * theta, phi);
+              f_type = false;
+            }
+            if (ok2 && filter_ok(tp.theta, tp.phi)) {
+              accepted = true;
+              alpha = a_soc;
+              for (int a = 0; a < 6; ++a) acc_newlam[a] = newlam[a];
+              for (int a = 0; a < 7; ++a) acc_newy0[a] = newy0[a];
+#pragma unroll
+              for (int r = 0; r < kNumRows; ++r) acc_dsr[r] = dss[r];
+              break;
+            }
+            if (tp.theta > o.kappa_soc * th_old) break;
+            th_old = tp.theta;
+            for (int a = 0; a < 6; ++a) c_soc[a] = a_soc * c_soc[a] + tp.c[a];
+#pragma unroll
+            for (int r = 0; r < kNumRows; ++r) d_soc[r] = a_soc * d_soc[r] + tp.rd[r];
+          }
+          if (accepted) break;
+          for (int a = 0; a < 6; ++a) dx[a] = dx0[a];
+          dsh = dsh0;
+          du[0] = du0[0];
+          du[1] = du0[1];
+        }
+        alpha *= o.alpha_red_factor;
+      }
+      if (!accepted) { status = kRestorationNeeded; break; }
+      if (!f_type) filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);
+      // ---- dual steps --------------------------------------------------------------------
+      // dyd = D ds + gsb - yd (with the ds of the accepted direction; for SOC its own rhs)
+      double az = 1.0;
+      double dvL[kNumRows], dvU[kNumRows], dyd[kNumRows];
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        dvL[r] = dvU[r] = dyd[r] = 0.0;
+        if (!on(r)) continue;
+        const double D = sigma_row(r) + dw;
+        dyd[r] = D * acc_dsr[r] + gsb_row(r) - yd[r];
+        if (row_hasL(r)) {
+          const double sl = s[r] - lo(r);
+          dvL[r] = mu / sl - vL[r] - vL[r] / sl * acc_dsr[r];
+          if (dvL[r] < 0.0) az = fmin(az, -tau * vL[r] / dvL[r]);
+        }
+        if (row_hasU(r)) {
+          const double su = hi(r) - s[r];
+          dvU[r] = mu / su - vU[r] + vU[r] / su * acc_dsr[r];
+          if (dvU[r] < 0.0) az = fmin(az, -tau * vU[r] / dvU[r]);
+        }
+      }
+      az = warp_min(az);
+      // ---- accept -------------------------------------------------------------------------
+      for (int a = 0; a < 6; ++a) {
+        x[a] = tp.x[a];
+        cres[a] = tp.c[a];
+        if (act) lam[a] += alpha * (acc_newlam[a] - lam[a]);
+      }
+      for (int a = 0; a < 7; ++a) y0[a] += alpha * (acc_newy0[a] - y0[a]);
+      sh = tp.sh;
+      u[0] = tp.u[0];
+      u[1] = tp.u[1];
+      fval = tp.f;
+      cur_finite = tp.finite;
+#pragma unroll
+      for (int r = 0; r < kNumRows; ++r) {
+        if (!on(r)) continue;
+        s[r] = tp.s[r];
+        rd[r] = tp.rd[r];
+        yd[r] += alpha * dyd[r];
+        if (row_hasL(r)) {
+          const double sl = s[r] - lo(r);
+          double v = vL[r] + az * dvL[r];
+          vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
+        }
+        if (row_hasU(r)) {
+          const double su = hi(r) - s[r];
+          double v = vU[r] + az * dvU[r];
+          vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
+        }
+      }
+      last_alpha = alpha;
+      it++;
+    }
+
+    // ---- outputs ---------------------------------------------------------------------------
+    {
+      double xp[6], shp, up[2];
+      gather_prev(x, sh, u, xp, shp, up);
+      StageCost sc;
+      stage_cost(p, pb.cx, pb.cy, xp, shp, 0, sc);
+      if (act) {
+        out.U[lane] = u[0];
+        out.U[N + lane] = u[1];
+        for (int a = 0; a < 6; ++a) out.X[a * (N + 1) + lane + 1] = x[a];
+        out.S[lane + 1] = sh;
+        out.eC[lane] = sc.eC;       // e_hat_C(S_hat[i], States[:, i]), i = 0..N-1
+        out.eL[lane] = sc.eL;
+      }
+      if (lane == 0) {
+        for (int a = 0; a < 6; ++a) out.X[a * (N + 1)] = pb.x0[a];
+        out.S[0] = pb.s0;
+        out.obj[0] = fval / df;
+        out.status[0] = status;
+        out.iters[0] = it;
+      }
+      if (out.lam_g) {
+        const int bs = 7 + (cfg.lane_con ? 1 : 0);
+        const int base2 = 7 + N * bs;
+        const double idf = 1.0 / df;
+        if (lane == 0) {
+          out.lam_g[0] = y0[6] * idf;
+          for (int a = 0; a < 6; ++a) out.lam_g[1 + a] = y0[a] * idf;
+        }
+        if (act) {
+          double* l1 = out.lam_g + 7 + lane * bs;     // rows of stage i = lane + 1
+          for (int a = 0; a < 6; ++a) l1[a] = lam[a] * idf;
+          l1[6] = yd[kProg] * idf;
+          if (cfg.lane_con) l1[7] = yd[kLane] * ddl * idf;
+          int off = cfg.wrap ? 6 * lane : (lane == 0 ? 0 : 4 + 6 * (lane - 1));
+          double* l2 = out.lam_g + base2 + off;
+          l2[0] = yd[kThrUb] * idf;
+          l2[1] = yd[kThrLb] * idf;
+          l2[2] = yd[kStUb] * idf;
+          l2[3] = yd[kStLb] * idf;
+          if (on(kDThr)) { l2[4] = yd[kDThr] * idf; l2[5] = yd[kDSt] * idf; }
+          if (lane == 0) {
+            double* l3 = out.lam_g + base2 + (cfg.wrap ? 6 * N : 6 * N - 2);
+            int q = 0;
+            if (on(kDThr0)) l3[q++] = yd[kDThr0] * idf;
+            if (on(kDSt0)) l3[q++] = yd[kDSt0] * idf;
+          }
+        }
+      }
+    }
+  }
+};
+
+
+// ---------------------------------------------------------------------------
+// One problem of a batch: load inputs, run the solver, store the outputs.
+// Called by every lane of a warp with the same arguments.
+// ---------------------------------------------------------------------------
+MPCR_HD int lam_g_stride(const Config& c) {
+  return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
+}
+
+MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
+                          int trace_rows, double* wsbase) {
+  const int N = cfg.N;
+  ProblemView pv;
+  for (int k = 0; k < 6; ++k) pv.x0[k] = in.x0[(size_t)b * 6 + k];
+  pv.u_prev[0] = in.u_prev[(size_t)b * 2 + 0];
+  pv.u_prev[1] = in.u_prev[(size_t)b * 2 + 1];
+  pv.has_prev_thr = pv.u_prev[0] == pv.u_prev[0];   // NaN = None (control/MPC.py:145-149)
+  pv.has_prev_st = pv.u_prev[1] == pv.u_prev[1];
+  pv.s0 = in.s0[b];
+  for (int k = 0; k < 5; ++k) { pv.cx[k] = in.cx[(size_t)b * 5 + k]; pv.cy[k] = in.cy[(size_t)b * 5 + k]; }
+  pv.max_err = in.max_err ? in.max_err[b] : 0.0;
+  pv.u_warm = in.u_warm ? in.u_warm + (size_t)b * 2 * N : nullptr;
+  if (!pv.has_prev_thr) pv.u_prev[0] = 0.0;
+  if (!pv.has_prev_st) pv.u_prev[1] = 0.0;
+  Params prm = cfg.p;
+  if (in.params) {
+    const double* q = in.params + (size_t)b * 5;
+    prm.alpha_c = q[0];
+    prm.d_max = q[1];
+    prm.q_v_y = q[2];
+    prm.n_exp = (int)(q[3] + 0.5);
+    prm.beta_delta = q[4];
+  }
+  SolveOut so;
+  so.U = out.U + (size_t)b * 2 * N;
+  so.X = out.X + (size_t)b * 6 * (N + 1);
+  so.S = out.S + (size_t)b * (N + 1);
+  so.eC = out.eC + (size_t)b * N;
+  so.eL = out.eL + (size_t)b * N;
+  so.lam_g = out.lam_g ? out.lam_g + (size_t)b * lam_g_stride(cfg) : nullptr;
+  so.obj = out.obj + b;
+  so.status = out.status + b;
+  so.iters = out.iters + b;
+  so.trace = out.trace ? out.trace + (size_t)b * trace_rows * kTraceCols : nullptr;
+  if (so.lam_g) {
+    const int ls = lam_g_stride(cfg);
+    for (int k = lane_id(); k < ls; k += 32) so.lam_g[k] = 0.0;
+    syncwarp();
+  }
+  WarpSolver solver(cfg, prm, pv, wsbase);
+  solver.solve(so);
+}
+
+}  // namespace mpcr

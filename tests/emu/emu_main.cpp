@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE ONLY: compiles the warp-level solver source for the host
+// with the SIMT emulator and exposes a batch entry point for ctypes.
+#define MPCR_EMU 1
+#include "simt_emu.h"
+
+#include <vector>
+
+#include "../../mpc_racing_b200/csrc/mpcr_config.h"
+#include "../../mpc_racing_b200/csrc/mpcr_ipm.cuh"
+
+namespace {
+struct Job {
+  const mpcr::Config* cfg;
+  const mpcr::BatchIn* in;
+  const mpcr::BatchOut* out;
+  int b;
+  int trace_rows;
+  double* ws;
+};
+void lane_body(void* p) {
+  Job* j = (Job*)p;
+  mpcr::solve_problem(*j->cfg, *j->in, *j->out, j->b, j->trace_rows, j->ws);
+}
+}  // namespace
+
+extern "C" int emu_lam_g_stride(const mpcr_config* c) {
+  mpcr::Config cfg;
+  mpcr::config_convert(*c, &cfg);
+  return mpcr::lam_g_stride(cfg);
+}
+
+extern "C" void emu_config_default(mpcr_config* c) { mpcr::config_default(c); }
+
+extern "C" int emu_solve_batch(const mpcr_config* c, int B, const double* x0, const double* u_prev,
+                               const double* s0, const double* cx, const double* cy,
+                               const double* max_err, const double* params, const double* u_warm,
+                               double* U, double* X, double* S, double* eC, double* eL,
+                               double* lam_g, double* obj, int32_t* status, int32_t* iters,
+                               double* trace) {
+  const char* why = nullptr;
+  if (!mpcr::config_valid(*c, &why)) return -1;
+  mpcr::Config cfg;
+  mpcr::config_convert(*c, &cfg);
+  mpcr::BatchIn in{x0, u_prev, s0, cx, cy, max_err, params, u_warm};
+  mpcr::BatchOut out{U, X, S, eC, eL, lam_g, obj, status, iters, trace};
+  std::vector<double> ws(mpcr::ws_doubles(cfg.N));
+  for (int b = 0; b < B; ++b) {
+    Job j{&cfg, &in, &out, b, cfg.o.max_iter + 1, ws.data()};
+    emu::run_warp(lane_body, &j);
+  }
+  return 0;
+}
+
+// stage-level debug entry: model value / Jacobian / Hessian for parity tests
+extern "C" void emu_model_lin(int model, const double* x, const double* u, double Ts,
+                              const double* lam, double* f, double* lin21, double* hm21) {
+  mpcr::StageLin L;
+  mpcr::lin_model(model, x, u, Ts, lam, f, L, hm21);
+  for (int k = 0; k < 3; ++k) { lin21[k] = L.aX[k]; lin21[3 + k] = L.aY[k]; }
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) lin21[6 + 3 * i + k] = L.d[i][k];
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 2; ++k) lin21[15 + 2 * i + k] = L.bu[i][k];
+}
