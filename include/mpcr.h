@@ -127,6 +127,10 @@ int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
 /* Launch geometry of the solve kernel: blocks, warps per block, dynamic shared bytes. */
 int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem_bytes);
 
+/* Measured fp64 FMA peak of the device (DFMA-chain microbenchmark, TFLOP/s):
+ * the roofline denominator for the solve kernel. */
+int mpcr_fp64_peak_tflops(mpcr_handle* h, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,7 @@ SOLVE_ARGTYPES = [C.c_void_p] * 8 + [C.c_void_p] * 9   # 8 inputs, 9 outputs (ra
 EXPORTED_SYMBOLS = [
     "mpcr_version", "mpcr_config_default", "mpcr_create", "mpcr_destroy", "mpcr_last_error",
     "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
-    "mpcr_launch_info",
+    "mpcr_launch_info", "mpcr_fp64_peak_tflops",
 ]
 
 _lib = None
@@ -81,6 +81,8 @@ def load_library(path=None):
     lib.mpcr_last_kernel_ms.restype = C.c_int
     lib.mpcr_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpcr_launch_info.restype = C.c_int
+    lib.mpcr_fp64_peak_tflops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.mpcr_fp64_peak_tflops.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

@@ -1,0 +1,199 @@
+"""Batched NMPC solve: the ``solve(states[B])`` entry point over the C ABI.
+
+``BatchedMPC`` owns one ``mpcr_handle`` (one CUDA device).  ``solve`` accepts
+either numpy arrays (host pointers; the library stages H2D/D2H itself - this is
+the end-to-end path) or torch CUDA tensors (device pointers; nothing leaves the
+GPU).  PyTorch is only plumbing here: device memory and streams.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .control.ControllerParameters import FixedControllerParameters, RuntimeControllerParameters
+
+MODEL_IDS = {"dynamic": 0, "kinematic": 1, "blended": 2}
+STATUS_NAMES = {0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level",
+                -1: "Maximum_Iterations_Exceeded", -2: "Restoration_Failed",
+                -3: "Error_In_Step_Computation", -4: "Invalid_Number_Detected"}
+
+
+@dataclass
+class BatchResult:
+    """Outputs of one batched solve, arrays on the side the inputs came from."""
+    U: object        # [B,2,N]
+    X: object        # [B,6,N+1]
+    S: object        # [B,N+1]
+    eC: object       # [B,N]
+    eL: object       # [B,N]
+    lam_g: object    # [B,stride] or None
+    obj: object      # [B]
+    status: object   # [B] int32
+    iters: object    # [B] int32
+    trace: object = None
+
+    @property
+    def converged(self):
+        return self.status >= 0
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class BatchedMPC:
+    """B independent progress-maximising NLPs (control/MPC.py) per call."""
+
+    def __init__(self, N: Optional[int] = None, Ts: Optional[float] = None, model="dynamic",
+                 fixed_params: Optional[FixedControllerParameters] = None,
+                 runtime_params: Optional[RuntimeControllerParameters] = None,
+                 wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
+                 tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False):
+        self.lib = _capi.load_library()
+        fp = fixed_params or FixedControllerParameters()
+        rp = runtime_params or RuntimeControllerParameters()
+        cfg = _capi.default_config(self.lib)
+        cfg.N = int(fp.N if N is None else N)
+        cfg.Ts = float(FixedControllerParameters.Ts if Ts is None else Ts)   # control/MPC.py:57
+        cfg.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
+        cfg.wrap_constraint = int(bool(wrap_constraint))
+        cfg.lane_constraint = int(bool(lane_constraint))
+        cfg.device = int(device)
+        cfg.pointers_on_device = int(bool(on_device))
+        cfg.max_iter = int(FixedControllerParameters.max_iter if max_iter is None else max_iter)
+        for name in ("lambda_s", "alpha_L", "min_steer", "max_steer", "min_throttle",
+                     "max_steer_delta", "min_steer_delta", "max_throttle_delta",
+                     "min_throttle_delta", "q_v_max", "v_max"):
+            setattr(cfg, name, float(getattr(fp, name)))
+        cfg.alpha_c = float(rp.alpha_c)
+        cfg.q_v_y = float(rp.q_v_y)
+        cfg.n_exp = float(rp.n)
+        cfg.beta_delta = float(rp.beta_delta)
+        # control/MPC.py:50 reads d_max from the CLASS, not the instance
+        cfg.d_max = float(rp.d_max if honor_instance_d_max else RuntimeControllerParameters.d_max)
+        cfg.tol = float(tol)
+        cfg.acceptable_tol = float(acceptable_tol)
+        self.cfg = cfg
+        self.N = cfg.N
+        self.on_device = bool(on_device)
+        self._h = C.c_void_p()
+        rc = self.lib.mpcr_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.mpcr_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                self.lib.mpcr_destroy(self._h)
+                self._h = C.c_void_p()
+            raise _capi.MpcrError(f"mpcr_create failed (rc={rc}) {msg}")
+        self.lam_g_stride = self.lib.mpcr_lam_g_stride(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.lib.mpcr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def launch_info(self):
+        b, w, s = C.c_int(), C.c_int(), C.c_int()
+        self.lib.mpcr_launch_info(self._h, C.byref(b), C.byref(w), C.byref(s))
+        return dict(blocks=b.value, warps_per_block=w.value, smem_bytes=s.value)
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._check(self.lib.mpcr_fp64_peak_tflops(self._h, C.byref(v)))
+        return v.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        rc = self.lib.mpcr_last_kernel_ms(self._h, C.byref(ms))
+        if rc != 0:
+            raise _capi.MpcrError(self.lib.mpcr_last_error(self._h).decode())
+        return ms.value
+
+    # ------------------------------------------------------------------
+    def solve(self, x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None,
+              want_lam_g=True, trace=False, stream=None, out=None) -> BatchResult:
+        if self.on_device:
+            return self._solve_device(x0, u_prev, s0, cx, cy, max_err, params, u_warm,
+                                      want_lam_g, trace, stream, out)
+        return self._solve_host(x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g,
+                                trace, stream, out)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _capi.MpcrError(f"mpcr_solve_batch failed (rc={rc}): "
+                                  f"{self.lib.mpcr_last_error(self._h).decode()}")
+
+    def _call(self, B, ins, outs, trace_ptr, stream):
+        args = [self._h, int(B)] + ins + outs
+        if trace_ptr is not None:
+            self._check(self.lib.mpcr_solve_batch_trace(*args, trace_ptr, stream))
+        else:
+            self._check(self.lib.mpcr_solve_batch(*args, stream))
+
+    def alloc_host_outputs(self, B, want_lam_g=True, pinned=False):
+        N, ls = self.N, self.lam_g_stride
+        shapes = dict(U=(B, 2, N), X=(B, 6, N + 1), S=(B, N + 1), eC=(B, N), eL=(B, N),
+                      lam_g=(B, ls), obj=(B,))
+        if pinned:
+            import torch
+            mk = lambda s, dt: torch.empty(s, dtype=dt).pin_memory().numpy()
+            o = {k: mk(s, torch.float64) for k, s in shapes.items()}
+            o["status"] = mk((B,), torch.int32)
+            o["iters"] = mk((B,), torch.int32)
+        else:
+            o = {k: np.empty(s, dtype=np.float64) for k, s in shapes.items()}
+            o["status"] = np.empty(B, dtype=np.int32)
+            o["iters"] = np.empty(B, dtype=np.int32)
+        if not want_lam_g:
+            o["lam_g"] = None
+        return o
+
+    def _solve_host(self, x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g, trace,
+                    stream, out):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x0, u_prev, s0, cx, cy, max_err, params, u_warm = map(
+            f, (x0, u_prev, s0, cx, cy, max_err, params, u_warm))
+        B = x0.shape[0]
+        N = self.N
+        assert x0.shape == (B, 6) and u_prev.shape == (B, 2) and s0.shape == (B,)
+        assert cx.shape == (B, 5) and cy.shape == (B, 5)
+        assert u_warm is None or u_warm.shape == (B, 2, N)
+        assert params is None or params.shape == (B, 5)
+        o = out or self.alloc_host_outputs(B, want_lam_g)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        tr = np.zeros((B, self.cfg.max_iter + 1, 8)) if trace else None
+        self._call(B, [ptr(a) for a in (x0, u_prev, s0, cx, cy, max_err, params, u_warm)],
+                   [ptr(o[k]) for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters")],
+                   ptr(tr) if trace else None, stream)
+        return BatchResult(trace=tr, **o)
+
+    def _solve_device(self, x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g, trace,
+                      stream, out):
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        for a in (x0, u_prev, s0, cx, cy, max_err, params, u_warm):
+            assert a is None or (_is_torch(a) and a.is_cuda and a.dtype == torch.float64
+                                 and a.is_contiguous()), "device mode needs contiguous cuda fp64"
+        B, N, ls = x0.shape[0], self.N, self.lam_g_stride
+        if out is None:
+            mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+            out = dict(U=mk(B, 2, N), X=mk(B, 6, N + 1), S=mk(B, N + 1), eC=mk(B, N), eL=mk(B, N),
+                       lam_g=mk(B, ls) if want_lam_g else None, obj=mk(B),
+                       status=torch.empty(B, dtype=torch.int32, device=dev),
+                       iters=torch.empty(B, dtype=torch.int32, device=dev))
+        tr = torch.zeros(B, self.cfg.max_iter + 1, 8, dtype=torch.float64, device=dev) if trace else None
+        ptr = lambda a: None if a is None else a.data_ptr()
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        self._call(B, [ptr(a) for a in (x0, u_prev, s0, cx, cy, max_err, params, u_warm)],
+                   [ptr(out[k]) for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters")],
+                   ptr(tr) if trace else None, stream)
+        return BatchResult(trace=tr, **out)

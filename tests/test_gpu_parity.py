@@ -1,0 +1,161 @@
+"""Parity tests proper: the CUDA path, through the C ABI, against the oracle."""
+import numpy as np
+import pytest
+
+from mpc_racing_b200.workload import load_fixture, make_batch
+from oracle import vehicle as V
+from parity_util import assert_parity, oracle_solve
+
+pytestmark = pytest.mark.gpu
+
+
+def _asdict(res):
+    return dict(U=res.U, X=res.X, S=res.S, eC=res.eC, eL=res.eL, lam_g=res.lam_g, obj=res.obj,
+                status=res.status, iters=res.iters)
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    return load_fixture("cfg2_shanghai_4096.npz")
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from mpc_racing_b200.solver import BatchedMPC
+    return BatchedMPC(N=30, Ts=0.05, model="dynamic")
+
+
+def test_parity_default_horizon(cfg2, solver):
+    idx = list(range(24))
+    res = _asdict(solver.solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx],
+                               cfg2['cy'][idx]))
+    for j, b in enumerate(idx):
+        ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b])
+        assert_parity(res, j, ref)
+
+
+def test_matches_emulated_kernel_logic(cfg2, solver):
+    """CUDA build vs the CPU emulation of the same source: identical iteration counts."""
+    from emu_util import emu_solve
+    idx = list(range(32, 64))
+    res = solver.solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx])
+    emu = emu_solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx])
+    assert (res.status == emu['status']).all()
+    assert np.mean(res.iters == emu['iters']) >= 0.9
+    same = res.iters == emu['iters']
+    assert np.abs(res.obj - emu['obj'])[same].max() <= 1e-9 * np.abs(emu['obj']).max()
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(model="kinematic"), dict(model=V.MODEL_KINEMATIC)),
+    (dict(wrap_constraint=False), dict(wrap=False)),
+])
+def test_parity_variants(cfg2, kw, okw):
+    from mpc_racing_b200.solver import BatchedMPC
+    s = BatchedMPC(N=30, Ts=0.05, **kw)
+    idx = [0, 1, 2, 3]
+    res = _asdict(s.solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx]))
+    for j, b in enumerate(idx):
+        ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b], **okw)
+        assert_parity(res, j, ref)
+
+
+def test_parity_lane_rows_and_production_horizon():
+    from mpc_racing_b200.solver import BatchedMPC
+    d = load_fixture("cfg3_t1_triple_512.npz")
+    s = BatchedMPC(N=30, Ts=0.05, lane_constraint=True)
+    idx = [0, 1, 2]
+    res = _asdict(s.solve(d['x0'][idx], d['u_prev'][idx], d['s0'][idx], d['cx'][idx], d['cy'][idx],
+                          max_err=d['max_err'][idx]))
+    for j, b in enumerate(idx):
+        ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], lane=True,
+                           max_error=float(d['max_err'][b]))
+        assert_parity(res, j, ref)
+    d = load_fixture("prod_t4_256.npz")
+    s = BatchedMPC(N=15, Ts=0.05)
+    idx = [0, 1, 2, 3]
+    res = _asdict(s.solve(d['x0'][idx], d['u_prev'][idx], d['s0'][idx], d['cx'][idx], d['cy'][idx]))
+    for j, b in enumerate(idx):
+        ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], N=15)
+        assert_parity(res, j, ref)
+
+
+def test_device_pointer_path_is_bit_identical(cfg2, solver):
+    import torch
+    from mpc_racing_b200.solver import BatchedMPC
+    B = 256
+    ds = BatchedMPC(N=30, Ts=0.05, on_device=True)
+    host = solver.solve(cfg2['x0'][:B], cfg2['u_prev'][:B], cfg2['s0'][:B], cfg2['cx'][:B], cfg2['cy'][:B])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[:B])).cuda()
+    dev = ds.solve(t(cfg2['x0']), t(cfg2['u_prev']), t(cfg2['s0']), t(cfg2['cx']), t(cfg2['cy']))
+    torch.cuda.synchronize()
+    for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters"):
+        assert np.array_equal(getattr(dev, k).cpu().numpy(), getattr(host, k)), k
+
+
+def test_full_size_properties(cfg2, solver):
+    """BASELINE config 2 at full size (4096): size-independent properties of a solution."""
+    B = 4096
+    r = solver.solve(cfg2['x0'], cfg2['u_prev'], cfg2['s0'], cfg2['cx'], cfg2['cy'])
+    conv = r.status >= 0
+    assert conv.mean() >= 0.97, conv.mean()
+    U, X, S = r.U[conv], r.X[conv], r.S[conv]
+    # dynamics residual of the returned trajectory (explicit Euler, control/MPC.py:186-229)
+    f = V.f_dynamic(np.moveaxis(X[:, :, :-1], 1, 2), np.moveaxis(U, 1, 2), 0.05)
+    assert np.abs(np.moveaxis(X[:, :, 1:], 1, 2) - f).max() <= 1e-4 * 1.01
+    # bounds (relaxed by IPOPT's 1e-8) and rate rows, incl. the wrap rows
+    assert U[:, 0].max() <= 0.85 + 1e-6 and U[:, 0].min() >= -1 - 1e-6
+    assert np.abs(U[:, 1]).max() <= 0.9 + 1e-6
+    dthr = U[:, 0] - np.roll(U[:, 0], 1, axis=1)
+    dst = U[:, 1] - np.roll(U[:, 1], 1, axis=1)
+    assert dthr.min() >= -0.4 - 1e-6 and dthr.max() <= 2 + 1e-6
+    assert np.abs(dst).max() <= 0.2 + 1e-6
+    ds = np.diff(S, axis=1)
+    assert ds.min() >= 0.1 - 1e-6 and ds.max() <= 2.5 + 1e-6
+    assert np.allclose(X[:, :, 0], cfg2['x0'][conv]) and np.allclose(S[:, 0], cfg2['s0'][conv])
+    assert np.abs(U[:, 0, 0] - cfg2['u_prev'][conv, 0]).max() <= 2.0 + 1e-6
+    # idempotence / determinism: a second launch returns bit-identical results
+    r2 = solver.solve(cfg2['x0'], cfg2['u_prev'], cfg2['s0'], cfg2['cx'], cfg2['cy'])
+    assert np.array_equal(r.U, r2.U) and np.array_equal(r.iters, r2.iters)
+    # batch-position independence: a permuted batch gives the permuted answers
+    perm = np.random.default_rng(0).permutation(B)[:512]
+    r3 = solver.solve(cfg2['x0'][perm], cfg2['u_prev'][perm], cfg2['s0'][perm], cfg2['cx'][perm], cfg2['cy'][perm])
+    assert np.array_equal(r3.U, r.U[perm]) and np.array_equal(r3.status, r.status[perm])
+
+
+def test_dropin_mpc_class(cfg2):
+    """The reference's constructor surface (control/MPC.py:10-22, :183-184)."""
+    from mpc_racing_b200.control.MPC import MPC
+    from mpc_racing_b200.control.ControllerParameters import RuntimeControllerParameters
+    from mpc_racing_b200.models import State
+    b = 3
+    x = cfg2['x0'][b]
+    st = State(x=x[0], y=x[1], yaw=x[2], v_x=x[3], v_y=x[4], yaw_dot=x[5],
+               throttle=cfg2['u_prev'][b, 0], steer=cfg2['u_prev'][b, 1])
+    mpc = MPC(state0=st, s0=cfg2['s0'][b], centerline_x_poly_coeffs=list(cfg2['cx'][b]),
+              centerline_y_poly_coeffs=list(cfg2['cy'][b]), max_error=float(cfg2['max_err'][b]),
+              runtime_params=RuntimeControllerParameters())
+    sol, ret, dual = mpc.solution()
+    States, U, S_hat, e_c, e_l = ret
+    assert States.shape == (6, 31) and U.shape == (2, 30) and S_hat.shape == (31,)
+    assert len(e_c) == 30 and len(e_l) == 30 and dual.shape == (13 * 30 + 9,)
+    assert sol is not None and sol.stats()['success']
+    ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b])
+    assert abs(sol.obj - ref['obj']) <= 1e-6 * abs(ref['obj'])
+    # warm-started receding-horizon call (agent.py:171-205): last_controls as list of tuples
+    last = [(t, s) for t, s in zip(U[0], U[1])]
+    mpc2 = MPC(state0=st, s0=cfg2['s0'][b], centerline_x_poly_coeffs=list(cfg2['cx'][b]),
+               centerline_y_poly_coeffs=list(cfg2['cy'][b]), max_error=1.0,
+               runtime_params=RuntimeControllerParameters(), last_controls=last, Ts=0.05, N=30)
+    assert mpc2.solution()[0] is not None
+    # failure convention: config 1 returns the last iterate with sol = None, dual = None
+    d = load_fixture("cfg1_test_mpc.npz")
+    x = d['x0'][0]
+    st1 = State(x=x[0], y=x[1], yaw=x[2], v_x=x[3], v_y=x[4], yaw_dot=x[5], throttle=.19, steer=0.63)
+    m1 = MPC(state0=st1, s0=69.6, centerline_x_poly_coeffs=list(d['cx'][0]),
+             centerline_y_poly_coeffs=list(d['cy'][0]), max_error=float(d['max_err'][0]),
+             runtime_params=RuntimeControllerParameters(), Ts=0.1, N=25)
+    s1, r1, d1 = m1.solution()
+    ref1 = oracle_solve(d['x0'][0], d['u_prev'][0], 69.6, d['cx'][0], d['cy'][0], N=25, Ts=0.1)
+    assert (s1 is None) == (ref1['status'] < 0)
+    assert r1[0].shape == (6, 26) and np.isfinite(r1[0]).all()
