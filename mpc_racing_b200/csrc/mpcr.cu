@@ -8,6 +8,8 @@
 // their warp immediately.  No tensor cores (9x9 / 3x3 fp64 blocks), no CPU path.
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <new>
 #include <string>
 
@@ -16,21 +18,37 @@
 
 namespace mpcr {
 
+// STAGE_GLOBAL: the per-stage Riccati storage lives in a per-block global slab (L1/L2
+// resident) instead of shared memory; shared memory then only holds the ~4 KB scratch.
+template <int MODEL, bool STAGE_GLOBAL>
 __global__ void __launch_bounds__(32, 1)
 solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
-             int trace_rows, int* __restrict__ counter) {
+             int trace_rows, int* __restrict__ counter, double* __restrict__ slabs) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
+  double* stage = STAGE_GLOBAL ? slabs + (size_t)blockIdx.x * stage_doubles(cfg.N) : nullptr;
   while (true) {
     int b = 0;
     if (lane == 0) b = atomicAdd(counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
-    solve_problem(cfg, in, out, b, trace_rows, smem);
+    solve_problem<MODEL>(cfg, in, out, b, trace_rows, smem, stage);
     __syncwarp();
   }
 }
 
+typedef void (*SolveKernelFn)(const Config, const BatchIn, const BatchOut, int, int, int*, double*);
+
+static SolveKernelFn pick_kernel(int model, bool stage_global) {
+  if (stage_global) {
+    if (model == kDynamic) return solve_kernel<kDynamic, true>;
+    if (model == kKinematic) return solve_kernel<kKinematic, true>;
+    return solve_kernel<kBlended, true>;
+  }
+  if (model == kDynamic) return solve_kernel<kDynamic, false>;
+  if (model == kKinematic) return solve_kernel<kKinematic, false>;
+  return solve_kernel<kBlended, false>;
+}
 
 // DFMA-chain microbenchmark: the measured fp64 roofline denominator
 // (MEASURED_PEAKS.json has no fp64 entry).  8 independent chains per thread.
@@ -57,6 +75,9 @@ struct mpcr_handle {
   int blocks_per_sm = 0;
   int smem_bytes = 0;
   int* d_counter = nullptr;
+  double* d_slabs = nullptr;
+  bool stage_global = false;
+  SolveKernelFn kernel = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // staging buffers for the host-pointer path
@@ -99,16 +120,29 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
-  h->smem_bytes = ws_doubles(h->cfg.N) * (int)sizeof(double);
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          cudaSharedmemCarveoutMaxShared));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, solve_kernel, 32,
+  {
+    const char* e = getenv("MPCR_STAGE_GLOBAL");
+    h->stage_global = e ? (atoi(e) != 0) : false;
+  }
+  h->kernel = pick_kernel(h->cfg.model, h->stage_global);
+  h->smem_bytes = (h->stage_global ? kScratch : ws_doubles(h->cfg.N)) * (int)sizeof(double);
+  CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  if (!h->stage_global)
+    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, 32,
                                                    h->smem_bytes));
   if (h->blocks_per_sm < 1) {
     h->err = "solve kernel does not fit on this device";
     return MPCR_ERR_CUDA;
   }
+  {
+    const char* e = getenv("MPCR_BLOCKS_PER_SM");
+    if (e && atoi(e) > 0 && atoi(e) < h->blocks_per_sm) h->blocks_per_sm = atoi(e);
+  }
+  if (h->stage_global)
+    CK(cudaMalloc(&h->d_slabs, (size_t)h->num_sms * h->blocks_per_sm * stage_doubles(h->cfg.N) *
+                                   sizeof(double)));
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
@@ -119,6 +153,7 @@ extern "C" int mpcr_destroy(mpcr_handle* h) {
   if (!h) return MPCR_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->d_counter) cudaFree(h->d_counter);
+  if (h->d_slabs) cudaFree(h->d_slabs);
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->d_ibuf) cudaFree(h->d_ibuf);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -155,7 +190,7 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
   if (grid > B) grid = B;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   CK(cudaEventRecord(h->ev0, st));
-  solve_kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter);
+  h->kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, h->d_slabs);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, st));
   h->timed = true;

@@ -78,6 +78,7 @@ constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
 constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
 constexpr int kScratch = 81 + 108 + 144 + 27 + 27 + 36 + kMisc;
 MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
+MPCR_HD int stage_doubles(int N) { return (N + 1) * kStride; }
 
 struct WarpWs {
   double* stage;  // [(N+1)][kStride]
@@ -88,9 +89,15 @@ struct WarpWs {
   double* tv;     // [3][9]
   double* gv;     // [3][12]
   double* misc;   // [kMisc]
-  MPCR_HD void bind(double* base, int N) {
-    stage = base;
-    P = base + (N + 1) * kStride;
+  // stage_base == nullptr: the stage storage lives in front of the scratch area at `base`
+  MPCR_HD void bind(double* base, double* stage_base, int N) {
+    if (stage_base) {
+      stage = stage_base;
+      P = base;
+    } else {
+      stage = base;
+      P = base + (N + 1) * kStride;
+    }
     T = P + 81;
     G = T + 108;
     pv = G + 144;
@@ -160,8 +167,10 @@ enum Row : int {
   kThrUb = 0, kThrLb = 1, kStUb = 2, kStLb = 3, kDThr = 4, kDSt = 5, kProg = 6,
   kDThr0 = 7, kDSt0 = 8, kLane = 9
 };
-MPCR_HD bool row_hasL(int r) { return r != kThrUb && r != kStUb; }
-MPCR_HD bool row_hasU(int r) { return r != kThrLb && r != kStLb; }
+constexpr unsigned kHasLMask = 0x3FAu;   // every row except thr_ub, st_ub has a lower bound
+constexpr unsigned kHasUMask = 0x3F5u;   // every row except thr_lb, st_lb has an upper bound
+MPCR_HD bool row_hasL(int r) { return (kHasLMask >> r) & 1u; }
+MPCR_HD bool row_hasU(int r) { return (kHasUMask >> r) & 1u; }
 
 struct ProblemView {     // uniform over the warp
   double x0[6];
@@ -178,15 +187,14 @@ struct SolveOut {        // pointers already offset to this problem
   double* obj; int32_t* status; int32_t* iters; double* trace;
 };
 
-MPCR_HD int lam_g_len(const Config& c, bool has_thr, bool has_st) {
-  int N = c.N;
-  return 7 + N * (7 + (c.lane_con ? 1 : 0)) + 4 * N + (c.wrap ? 2 * N : 2 * (N - 1)) +
-         (has_thr ? 1 : 0) + (has_st ? 1 : 0);
-}
+// solver phases: every heavy routine has exactly ONE call site inside the phase loop
+// (keeps the kernel's instruction footprint inside the SM instruction cache)
+enum Phase : int { kPhInit = 0, kPhInit2 = 1, kPhNewton = 2, kPhBacktrack = 3, kPhSoc = 4 };
 
 // ---------------------------------------------------------------------------
-// The solver.  All members are per-lane registers unless noted "uniform".
+// The solver.  All members are per-lane unless noted "uniform".
 // ---------------------------------------------------------------------------
+template <int MODEL>
 struct WarpSolver {
   const Config& cfg;
   const Params& p;        // per-problem copy (GA sweeps override the runtime parameters)
@@ -202,35 +210,32 @@ struct WarpSolver {
   double dcs[6];            // gradient-based row scaling of the dynamics rows
   double ddl;               // same for the lane row
   double df;                // objective scaling (uniform)
-  // slack rows
+  // slack rows (runtime-indexed -> local memory)
   unsigned rowmask;
   double s[kNumRows], yd[kNumRows], vL[kNumRows], vU[kNumRows];
   double rd[kNumRows];      // d_r(x) - s_r at the current iterate
   double cres[6];           // x_{k+1} - f(x_k, u_k) at the current iterate
-  double fval;              // df * f(x) (uniform)
+  double fval, barB;        // df * f(x); barrier sum B(s): phi = fval + mu * barB (uniform)
   // search direction
   double dx[6], dsh, du[2];
+  double dsr[kNumRows];
   double mu, tau;
   // filter: one entry per lane
   double filt_th, filt_ph;
   int filt_n;
   int gslot[5];
 
-  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, double* wsbase)
+  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, double* wsbase,
+                    double* stagebase)
       : cfg(c), p(prm), o(c.o), pb(pv) {
     lane = lane_id();
     N = c.N;
     act = lane < N;
-    ws.bind(wsbase, N);
+    ws.bind(wsbase, stagebase, N);
     for (int j = 0; j < 5; ++j) {
       int e = lane + 32 * j;
       int slot = 0xff;
-      if (e < 144) {
-        int rr = e / 12, cc = e % 12;
-        int sl = hs_slot(rr, cc);
-        slot = (sl < 0) ? 0xff : sl;
-        if (rr == cc && (rr <= 6 || rr == 9 || rr == 10)) slot |= 0x100;   // gets +delta_w
-      }
+      if (e < 144) slot = slot_of(e / 12, e % 12);
       gslot[j] = slot;
     }
   }
@@ -270,9 +275,9 @@ struct WarpSolver {
       default: return ddl * eC;
     }
   }
-  // J_r * (step), the row's linear form applied to a direction
+  // J_r * (step): the row's linear form applied to a direction
   MPCR_D double row_lin(int r, const double* duu, const double* dup, double dshh, double dshp,
-                        const double* dxy /* dX, dY of the lane's state */) const {
+                        const double* dxy) const {
     switch (r) {
       case kThrUb: case kThrLb: case kDThr0: return duu[0];
       case kStUb: case kStLb: case kDSt0: return duu[1];
@@ -297,49 +302,27 @@ struct WarpSolver {
     up[1] = shfl(uu[1], src);
   }
 
-  MPCR_D double barrier_terms(const double* ss) const {
-    double acc = 0.0;
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) {
-      if (!on(r)) continue;
-      double t = 0.0;
-      if (row_hasL(r)) {
-        double sl = ss[r] - lo(r);
-        t -= mu * log(sl);
-        if (!row_hasU(r)) t += o.kappa_d * mu * sl;
-      }
-      if (row_hasU(r)) {
-        double su = hi(r) - ss[r];
-        t -= mu * log(su);
-        if (!row_hasL(r)) t += o.kappa_d * mu * su;
-      }
-      acc += t;
-    }
-    return acc;
-  }
-
   // -------------------------------------------------------------------------
   // objective / constraints at a point (line search trial or current iterate)
   // -------------------------------------------------------------------------
   struct Point {
     double x[6], sh, u[2], s[kNumRows];
     double c[6], rd[kNumRows];
-    double f, theta, phi;   // uniform
+    double f, theta, barB;  // uniform
     bool finite;            // uniform
   };
 
-  MPCR_D void eval_point(Point& t, bool with_slacks) const {
+  MPCR_D void eval_point(Point& t) const {
     double xp[6], shp, up[2];
     gather_prev(t.x, t.sh, t.u, xp, shp, up);
     double f[6];
-    f_model(cfg.model, xp, t.u, cfg.Ts, f);
+    f_model(MODEL, xp, t.u, cfg.Ts, f);
     StageCost sc;
     stage_cost(p, pb.cx, pb.cy, t.x, t.sh, 0, sc);
     double fl = 0.0, th = 0.0;
+    double prod = 1.0, lin = 0.0;       // barrier: -log(prod of slack distances) + kappa_d * lin
     bool fin = true;
     for (int k = 0; k < 6; ++k) t.c[k] = 0.0;
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) t.rd[r] = 0.0;
     if (act) {
       fl = sc.val;
       if (lane == N - 1) fl -= p.lambda_s * t.sh;
@@ -351,24 +334,35 @@ struct WarpSolver {
         t.c[k] = t.x[k] - f[k];
         th += fabs(dcs[k] * t.c[k]);
       }
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) {
-        if (!on(r)) continue;
-        double v = row_value(r, t.u, up, t.sh, shp, sc.eC);
-        t.rd[r] = with_slacks ? v - t.s[r] : v;
-        th += fabs(t.rd[r]);
-      }
-      fin = finite_d(fl) && finite_d(th);
     }
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r) {
+      double rdv = 0.0;
+      if (on(r)) {
+        const double sv = t.s[r];
+        rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
+        th += fabs(rdv);
+        if (row_hasL(r)) {
+          const double sl = sv - lo(r);
+          prod *= sl;
+          if (!row_hasU(r)) lin += sl;
+          if (!(sl > 0.0)) fin = false;
+        }
+        if (row_hasU(r)) {
+          const double su = hi(r) - sv;
+          prod *= su;
+          if (!row_hasL(r)) lin += su;
+          if (!(su > 0.0)) fin = false;
+        }
+      }
+      t.rd[r] = rdv;
+    }
+    double bar = act ? (-log(prod) + o.kappa_d * lin) : 0.0;
+    fin = fin && finite_d(fl) && finite_d(th) && finite_d(bar);
     t.finite = warp_all(fin);
     t.f = df * warp_sum(fl);
     t.theta = warp_sum(th);
-    t.phi = 0.0;
-    if (with_slacks) {
-      double bar = act ? barrier_terms(t.s) : 0.0;
-      t.phi = t.f + warp_sum(bar);
-      if (!finite_d(t.phi)) t.finite = false;
-    }
+    t.barB = warp_sum(bar);
   }
 
   // -------------------------------------------------------------------------
@@ -384,8 +378,9 @@ struct WarpSolver {
     double xp[6], shp, up[2];
     gather_prev(x, sh, u, xp, shp, up);
     double hm[kHmDoubles];
-    double zero6[6] = {0, 0, 0, 0, 0, 0};
-    lin_model(cfg.model, xp, u, cfg.Ts, mode == 0 ? lam : zero6, nullptr, lin, hm);
+    double lz[6];
+    for (int k = 0; k < 6; ++k) lz[k] = (mode == 0) ? lam[k] : 0.0;
+    lin_model(MODEL, xp, u, cfg.Ts, lz, nullptr, lin, hm);
     StageCost sc;
     stage_cost(p, pb.cx, pb.cy, x, sh, 2, sc);
     gcost[0] = df * sc.g3[0];
@@ -447,40 +442,43 @@ struct WarpSolver {
   // -------------------------------------------------------------------------
   double Dw[2];   // D of the two wrap rows (uniform, from lane 0)
 
-  MPCR_D double sigma_row(int r) const {
-    double sg = 0.0;
-    if (row_hasL(r)) sg += vL[r] / (s[r] - lo(r));
-    if (row_hasU(r)) sg += vU[r] / (hi(r) - s[r]);
-    return sg;
-  }
-  MPCR_D double gsb_row(int r) const {   // d(barrier objective)/d(slack r)
-    double g = 0.0;
+  // Sigma_r and d(barrier objective)/d(slack r)
+  MPCR_D void sigma_gsb(int r, double& sg, double& g) const {
+    sg = 0.0;
+    g = 0.0;
     if (row_hasL(r)) {
-      g -= mu / (s[r] - lo(r));
+      const double isl = 1.0 / (s[r] - lo(r));
+      sg += vL[r] * isl;
+      g -= mu * isl;
       if (!row_hasU(r)) g += o.kappa_d * mu;
     }
     if (row_hasU(r)) {
-      g += mu / (hi(r) - s[r]);
+      const double isu = 1.0 / (hi(r) - s[r]);
+      sg += vU[r] * isu;
+      g += mu * isu;
       if (!row_hasL(r)) g -= o.kappa_d * mu;
     }
-    return g;
   }
 
   MPCR_D void write_row_terms(int mode, double dw, const double* rdv /* [kNumRows] */,
                               const double* cv /* [6] dynamics rhs */) {
     double D[kNumRows], e[kNumRows];
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
-      D[r] = 0.0;
-      e[r] = 0.0;
-      if (!on(r) || !act) continue;
-      if (mode == 0) {
-        D[r] = sigma_row(r) + dw;
-        e[r] = D[r] * rdv[r] + gsb_row(r);
-      } else {
-        D[r] = 1.0;
-        e[r] = -((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0));
+      double Dr = 0.0, er = 0.0;
+      if (on(r)) {
+        if (mode == 0) {
+          double sg, g;
+          sigma_gsb(r, sg, g);
+          Dr = sg + dw;
+          er = Dr * rdv[r] + g;
+        } else {
+          Dr = 1.0;
+          er = -((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0));
+        }
       }
+      D[r] = Dr;
+      e[r] = er;
     }
     const bool wrap0 = (lane == 0);   // rows kDThr/kDSt of lane 0 are the non-local wrap rows
     double Dw0 = shfl(D[kDThr], 0), Dw1 = shfl(D[kDSt], 0);
@@ -578,7 +576,7 @@ struct WarpSolver {
     if (slot & 0x100) v += dw;
     return v;
   }
-  MPCR_D int slot_of(int r, int c) const {
+  MPCR_D static int slot_of(int r, int c) {
     int sl = hs_slot(r, c);
     int slot = (sl < 0) ? 0xff : sl;
     if (r == c && (r <= 6 || r == 9 || r == 10)) slot |= 0x100;
@@ -616,6 +614,7 @@ struct WarpSolver {
     }
     syncwarp();
     bool ok = true;
+#pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
       double* st = ws.st(k);
       // ---- round 1: T = P M (rows), t_j = p_j + P b_j ; G <- stage Hessian ----
@@ -637,28 +636,25 @@ struct WarpSolver {
       }
       syncwarp();
       // ---- round 2: G[:, c] += M' T[:, c] ; g_j = grad_j + M' t_j -----------------
-      if (lane < 12) {
-        if (lane != 7 && lane != 8) {
-          double tc[9], A[21], out[12];
-          for (int r = 0; r < 9; ++r) tc[r] = T[r * 12 + lane];
-          for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
-          mulM(tc, A, Ts, out);
-          for (int r = 0; r < 12; ++r) G[r * 12 + lane] += out[r];
-        }
-      } else if (lane < 12 + nrhs) {
+      if (lane < 12 + nrhs && lane != 7 && lane != 8) {
+        const bool isvec = lane >= 12;
         const int j = lane - 12;
         double tc[9], A[21], out[12];
-        for (int r = 0; r < 9; ++r) tc[r] = ws.tv[j * 9 + r];
+        for (int r = 0; r < 9; ++r) tc[r] = isvec ? ws.tv[j * 9 + r] : T[r * 12 + lane];
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(tc, A, Ts, out);
-        for (int r = 0; r < 12; ++r) {
-          double g = out[r];
-          if (j == 0) g += st[kOffGs + r];
-          ws.gv[j * 12 + r] = g;
-        }
-        if (j >= 1) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
-          double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
-          ws.gv[j * 12 + 9 + (j - 1)] += a;
+        if (!isvec) {
+          for (int r = 0; r < 12; ++r) G[r * 12 + lane] += out[r];
+        } else {
+          for (int r = 0; r < 12; ++r) {
+            double g = out[r];
+            if (j == 0) g += st[kOffGs + r];
+            ws.gv[j * 12 + r] = g;
+          }
+          if (j >= 1) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
+            double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
+            ws.gv[j * 12 + 9 + (j - 1)] += a;
+          }
         }
       }
       syncwarp();
@@ -677,34 +673,27 @@ struct WarpSolver {
       // identical in every lane (same inputs, same arithmetic) -> uniform branch
       if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) { ok = false; break; }
       if (lane < 9 || (lane >= 12 && lane < 12 + nrhs)) {
-        double r0, r1, r2;
+        const bool isvec = lane >= 12;
         const int c = lane;
         const int j = lane - 12;
-        if (lane < 9) {
-          r0 = G[9 * 12 + c]; r1 = G[10 * 12 + c]; r2 = G[11 * 12 + c];
-        } else {
-          r0 = ws.gv[j * 12 + 9]; r1 = ws.gv[j * 12 + 10]; r2 = ws.gv[j * 12 + 11];
-        }
+        const double* src = isvec ? (ws.gv + j * 12) : (G + c);
+        const int sstride = isvec ? 1 : 12;
+        const double r0 = src[9 * sstride], r1 = src[10 * sstride], r2 = src[11 * sstride];
         const double f0 = r0, f1 = r1 - l10 * f0, f2 = r2 - l20 * f0 - l21 * f1;
         const double z2 = f2 * id2;
         const double z1 = f1 * id1 - l21 * z2;
         const double z0 = f0 * id0 - l10 * z1 - l20 * z2;
         const double k0 = -z0, k1 = -z1, k2 = -z2;
-        if (lane < 9) {
-          st[kOffK + 0 * 9 + c] = k0;
-          st[kOffK + 1 * 9 + c] = k1;
-          st[kOffK + 2 * 9 + c] = k2;
-          for (int a = 0; a < 9; ++a)
-            P[a * 9 + c] = G[a * 12 + c] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
-                           G[11 * 12 + a] * k2;
-        } else {
-          st[kOffKf + j * 3 + 0] = k0;
-          st[kOffKf + j * 3 + 1] = k1;
-          st[kOffKf + j * 3 + 2] = k2;
-          for (int a = 0; a < 9; ++a)
-            ws.pv[j * 9 + a] = ws.gv[j * 12 + a] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
-                               G[11 * 12 + a] * k2;
-        }
+        double* kdst = isvec ? (st + kOffKf + j * 3) : (st + kOffK + c);
+        const int kstride = isvec ? 1 : 9;
+        kdst[0] = k0;
+        kdst[kstride] = k1;
+        kdst[2 * kstride] = k2;
+        double* pdst = isvec ? (ws.pv + j * 9) : (P + c);
+        const int pstride = isvec ? 1 : 9;
+        for (int a = 0; a < 9; ++a)
+          pdst[a * pstride] = src[a * sstride] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
+                              G[11 * 12 + a] * k2;
       }
       syncwarp();
     }
@@ -716,26 +705,30 @@ struct WarpSolver {
       for (int a = 0; a < 7; ++a) mz[j][a] = 0.0;
       mw[j][0] = mw[j][1] = 0.0;
     }
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
       const double* st = ws.st(k);
       double A[21];
       for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
-      for (int j = 0; j < nrhs; ++j) {
-        double w[3];
-        for (int i = 0; i < 3; ++i) {
-          double acc = st[kOffKf + j * 3 + i];
-          for (int a = 0; a < 9; ++a) acc += st[kOffK + i * 9 + a] * z[j][a];
-          w[i] = acc;
-        }
-        double zn[9];
-        applyM(z[j], w, A, Ts, zn);
-        if (j == 0)
-          for (int a = 0; a < 6; ++a) zn[a] += st[kOffB + a];
-        for (int a = 0; a < 9; ++a) z[j][a] = zn[a];
-        if (k == lane) {
-          for (int a = 0; a < 7; ++a) mz[j][a] = zn[a];
-          mw[j][0] = w[0];
-          mw[j][1] = w[1];
+#pragma unroll
+      for (int j = 0; j < kRhs; ++j) {
+        if (j < nrhs) {
+          double w[3];
+          for (int i = 0; i < 3; ++i) {
+            double acc = st[kOffKf + j * 3 + i];
+            for (int a = 0; a < 9; ++a) acc += st[kOffK + i * 9 + a] * z[j][a];
+            w[i] = acc;
+          }
+          double zn[9];
+          applyM(z[j], w, A, Ts, zn);
+          if (j == 0)
+            for (int a = 0; a < 6; ++a) zn[a] += st[kOffB + a];
+          for (int a = 0; a < 9; ++a) z[j][a] = zn[a];
+          if (k == lane) {
+            for (int a = 0; a < 7; ++a) mz[j][a] = zn[a];
+            mw[j][0] = w[0];
+            mw[j][1] = w[1];
+          }
         }
       }
     }
@@ -816,6 +809,7 @@ struct WarpSolver {
     for (int a = 0; a < 6; ++a) newlam[a] = 0.0;
     if (lane == N - 1)
       for (int a = 0; a < 6; ++a) newlam[a] = -pi[a];
+#pragma unroll 1
     for (int j = N - 1; j >= 0; --j) {
       const double* st = ws.st(j);
       const double *aX = st + kOffA, *aY = st + kOffA + 3, *d = st + kOffA + 6;
@@ -855,7 +849,6 @@ struct WarpSolver {
     mulM(lv, A, cfg.Ts, out);
     const bool last = (lane == N - 1);
     double dinf = 0.0;
-    // x_{k+1}
     double txn[6];
     for (int a = 0; a < 6; ++a) {
       double t = shfl(out[a], next_lane());
@@ -889,24 +882,24 @@ struct WarpSolver {
         prinf = fmax(prinf, fabs(dcs[a] * cres[a]));
         sum_y += fabs(lam[a] / dcs[a]);
       }
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) {
-        if (!on(r)) continue;
-        double rs = -yd[r];
-        if (row_hasL(r)) {
-          rs -= vL[r];
-          cmpl = fmax(cmpl, fabs((s[r] - lo(r)) * vL[r] - mu_t));
-          sum_v += fabs(vL[r]);
-        }
-        if (row_hasU(r)) {
-          rs += vU[r];
-          cmpl = fmax(cmpl, fabs((hi(r) - s[r]) * vU[r] - mu_t));
-          sum_v += fabs(vU[r]);
-        }
-        dinf = fmax(dinf, fabs(rs));
-        prinf = fmax(prinf, fabs(rd[r]));
-        sum_y += fabs(yd[r]);
+    }
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r) {
+      if (!on(r)) continue;
+      double rs = -yd[r];
+      if (row_hasL(r)) {
+        rs -= vL[r];
+        cmpl = fmax(cmpl, fabs((s[r] - lo(r)) * vL[r] - mu_t));
+        sum_v += fabs(vL[r]);
       }
+      if (row_hasU(r)) {
+        rs += vU[r];
+        cmpl = fmax(cmpl, fabs((hi(r) - s[r]) * vU[r] - mu_t));
+        sum_v += fabs(vU[r]);
+      }
+      dinf = fmax(dinf, fabs(rs));
+      prinf = fmax(prinf, fabs(rd[r]));
+      sum_y += fabs(yd[r]);
     }
     Errors e;
     e.dual_inf = warp_max(dinf);
@@ -924,30 +917,28 @@ struct WarpSolver {
   // max violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
   MPCR_D double orig_violation() const {
     double v = 0.0;
-    if (act) {
+    if (act)
       for (int a = 0; a < 6; ++a) v = fmax(v, fabs(cres[a]));
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) {
-        if (!on(r)) continue;
-        double l, h;
-        row_bounds(r, l, h);
-        double val = rd[r] + s[r];
-        if (r == kLane) val /= ddl;
-        if (row_hasL(r)) v = fmax(v, l - val);
-        if (row_hasU(r)) v = fmax(v, val - h);
-      }
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r) {
+      if (!on(r)) continue;
+      double l, h;
+      row_bounds(r, l, h);
+      double val = rd[r] + s[r];
+      if (r == kLane) val /= ddl;
+      if (row_hasL(r)) v = fmax(v, l - val);
+      if (row_hasU(r)) v = fmax(v, val - h);
     }
     return warp_max(v);
   }
 
   MPCR_D double theta_local() const {
     double th = 0.0;
-    if (act) {
+    if (act)
       for (int a = 0; a < 6; ++a) th += fabs(dcs[a] * cres[a]);
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r)
-        if (on(r)) th += fabs(rd[r]);
-    }
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r)
+      if (on(r)) th += fabs(rd[r]);
     return th;
   }
 
@@ -965,33 +956,25 @@ struct WarpSolver {
     return a - b <= 10.0 * 2.220446049250313e-16 * fabs(ref);
   }
 
-  // fraction-to-the-boundary step for the slacks given ds (per row), and for v
-  MPCR_D double ftb_primal(const double* dsr) const {
-    double a = 1.0;
-    if (act) {
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) {
-        if (!on(r)) continue;
-        if (row_hasL(r) && dsr[r] < 0.0) a = fmin(a, -tau * (s[r] - lo(r)) / dsr[r]);
-        if (row_hasU(r) && dsr[r] > 0.0) a = fmin(a, tau * (hi(r) - s[r]) / dsr[r]);
-      }
-    }
-    return warp_min(a);
-  }
-
-  MPCR_D void slack_steps(const double* rdv, double* dsr) const {
-    // ds_r = J_r dx + rdv_r
+  // slack steps ds_r = J_r dx + rdv_r (into dsr) and the fraction-to-the-boundary step
+  MPCR_D double slack_steps(const double* rdv) {
     double dup[2], dshp;
     dup[0] = shfl(du[0], prev_lane());
     dup[1] = shfl(du[1], prev_lane());
     double t = shfl(dsh, prev_lane());
     dshp = (lane == 0) ? 0.0 : t;
-#pragma unroll
+    double a = 1.0;
+#pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
-      dsr[r] = 0.0;
-      if (!on(r) || !act) continue;
-      dsr[r] = row_lin(r, du, dup, dsh, dshp, dx) + rdv[r];
+      double d = 0.0;
+      if (on(r)) {
+        d = row_lin(r, du, dup, dsh, dshp, dx) + rdv[r];
+        if (row_hasL(r) && d < 0.0) a = fmin(a, -tau * (s[r] - lo(r)) / d);
+        if (row_hasU(r) && d > 0.0) a = fmin(a, tau * (hi(r) - s[r]) / d);
+      }
+      dsr[r] = d;
     }
+    return warp_min(a);
   }
 
   // -------------------------------------------------------------------------
@@ -1018,6 +1001,7 @@ struct WarpSolver {
       u[1] = act ? u1 : 0.0;
       double xr[6];
       for (int k = 0; k < 6; ++k) { xr[k] = pb.x0[k]; x[k] = pb.x0[k]; }
+#pragma unroll 1
       for (int k = 0; k < N; ++k) {
         double uk[2] = {shfl(u[0], k), shfl(u[1], k)};
         double fn[6];
@@ -1028,10 +1012,16 @@ struct WarpSolver {
       }
       sh = act ? pb.s0 + (lane + 1) * cfg.Ts * p.v_max : pb.s0;
     }
-    for (int k = 0; k < 6; ++k) { lam[k] = 0.0; dcs[k] = 1.0; cres[k] = 0.0; }
+    for (int k = 0; k < 6; ++k) { lam[k] = 0.0; dcs[k] = 1.0; cres[k] = 0.0; dx[k] = 0.0; }
     for (int k = 0; k < 7; ++k) y0[k] = 0.0;
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) { s[r] = 0.0; yd[r] = 0.0; vL[r] = 0.0; vU[r] = 0.0; rd[r] = 0.0; }
+    dsh = 0.0;
+    du[0] = du[1] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r) {
+      s[r] = 0.0; yd[r] = 0.0; rd[r] = 0.0; dsr[r] = 0.0;
+      vL[r] = (on(r) && row_hasL(r)) ? o.bound_mult_init_val : 0.0;
+      vU[r] = (on(r) && row_hasU(r)) ? o.bound_mult_init_val : 0.0;
+    }
     df = 1.0;
     ddl = 1.0;
     mu = o.mu_init;
@@ -1039,362 +1029,399 @@ struct WarpSolver {
     filt_n = 0;
     filt_th = 0.0;
     filt_ph = 0.0;
-    // counts
+    fval = 0.0;
+    barB = 0.0;
     {
       int nr = 0, nb = 0;
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < kNumRows; ++r)
         if (on(r)) { nr += 1; nb += (row_hasL(r) ? 1 : 0) + (row_hasU(r) ? 1 : 0); }
       n_eq_ineq = (int)(warp_sum((double)nr) + 0.5) + 6 * N + 7;
       n_bounds = (int)(warp_sum((double)nb) + 0.5);
     }
-    // ---- gradient-based scaling at the starting point -------------------------------
-    eval_derivs(1);
-    {
-      double sig_n_raw = shfl(sigc_prev, next_lane());
-      double sig_n = (lane == N - 1) ? 0.0 : sig_n_raw;
-      double g = 0.0;
-      if (act) {
-        for (int k = 0; k < 5; ++k) g = fmax(g, fabs(gcost[k]));
-        g = fmax(g, fabs(2.0 * p.beta_delta * (sigc_prev - sig_n)));
-      }
-      g = warp_max(g);
-      if (g > o.nlp_scaling_max_gradient)
-        df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
-      double rm[6];
-      rm[0] = fmax(1.0, fmax(fabs(lin.aX[0]), fmax(fabs(lin.aX[1]), fabs(lin.aX[2]))));
-      rm[1] = fmax(1.0, fmax(fabs(lin.aY[0]), fmax(fabs(lin.aY[1]), fabs(lin.aY[2]))));
-      rm[2] = fmax(1.0, fabs(cfg.Ts));
-      for (int i = 0; i < 3; ++i) {
-        double m = 1.0;
-        for (int k = 0; k < 3; ++k) m = fmax(m, fabs(lin.d[i][k]));
-        for (int k = 0; k < 2; ++k) m = fmax(m, fabs(lin.bu[i][k]));
-        rm[3 + i] = m;
-      }
-      for (int k = 0; k < 6; ++k)
-        dcs[k] = (rm[k] > o.nlp_scaling_max_gradient)
-                     ? fmax(o.nlp_scaling_max_gradient / rm[k], o.nlp_scaling_min_value) : 1.0;
-      double gl = fmax(fabs(gC[0]), fmax(fabs(gC[1]), fabs(gC[2])));
-      if (cfg.lane_con && gl > o.nlp_scaling_max_gradient)
-        ddl = fmax(o.nlp_scaling_max_gradient / gl, o.nlp_scaling_min_value);
-    }
-    // ---- relaxed bounds (uniform rows in shared; the lane row scales per lane -> ddl
-    //      is made uniform by using the warp minimum) ------------------------------------
-    ddl = warp_min(act ? ddl : 1.0);
-    if (lane < kNumRows) {
-      double l, h;
-      row_bounds(lane, l, h);
-      if (lane == kLane) { l *= ddl; h *= ddl; }
-      if (row_hasL(lane)) l -= fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(l)));
-      else l = -inf;
-      if (row_hasU(lane)) h += fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(h)));
-      else h = inf;
-      ws.misc[lane] = l;
-      ws.misc[kNumRows + lane] = h;
-    }
+    // provisional (unscaled, unrelaxed) bounds so that lo()/hi() are defined early
+    if (lane < kNumRows) { ws.misc[lane] = -inf; ws.misc[kNumRows + lane] = inf; }
     syncwarp();
-    // ---- slacks pushed into their bounds ---------------------------------------------
-    Point cur;
-    for (int k = 0; k < 6; ++k) cur.x[k] = x[k];
-    cur.sh = sh;
-    cur.u[0] = u[0];
-    cur.u[1] = u[1];
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) cur.s[r] = 0.0;
-    eval_point(cur, false);
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) {
-      if (!on(r)) { s[r] = 0.0; continue; }
-      double v = cur.rd[r];
-      const double l = lo(r), h = hi(r);
-      double pl, pu;
-      if (row_hasL(r) && row_hasU(r)) {
-        pl = fmin(o.bound_push * fmax(1.0, fabs(l)), o.bound_frac * (h - l));
-        pu = fmin(o.bound_push * fmax(1.0, fabs(h)), o.bound_frac * (h - l));
-      } else {
-        pl = o.bound_push * fmax(1.0, fabs(l));
-        pu = o.bound_push * fmax(1.0, fabs(h));
-      }
-      if (row_hasL(r)) v = fmax(v, l + pl);
-      if (row_hasU(r)) v = fmin(v, h - pu);
-      s[r] = v;
-      vL[r] = row_hasL(r) ? o.bound_mult_init_val : 0.0;
-      vU[r] = row_hasU(r) ? o.bound_mult_init_val : 0.0;
-    }
-    // ---- least-squares equality multipliers -----------------------------------------
-    eval_derivs(1);
-    {
-      double zr[kNumRows], zc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) zr[r] = 0.0;
-      write_row_terms(1, 1.0, zr, zc);
-      syncwarp();
-      bool ok = kkt_solve(1.0);
-      double dsr[kNumRows];
-      slack_steps(zr, dsr);     // J_d dx
-      double ymax = 0.0;
-      if (ok && act) {
-        for (int a = 0; a < 6; ++a) { lam[a] = -newlam[a]; ymax = fmax(ymax, fabs(lam[a] / dcs[a])); }
-#pragma unroll
-        for (int r = 0; r < kNumRows; ++r) {
-          if (!on(r)) continue;
-          yd[r] = ((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0)) - dsr[r];
-          ymax = fmax(ymax, fabs(yd[r]));
-        }
-      }
-      for (int a = 0; a < 7; ++a) { y0[a] = ok ? -newy0[a] : 0.0; ymax = fmax(ymax, fabs(y0[a])); }
-      ymax = warp_max(ymax);
-      if (!ok || !(ymax <= o.constr_mult_init_max)) {
-        for (int a = 0; a < 6; ++a) lam[a] = 0.0;
-        for (int a = 0; a < 7; ++a) y0[a] = 0.0;
-#pragma unroll
-        for (int r = 0; r < kNumRows; ++r) yd[r] = 0.0;
-      }
-    }
-    // ---- current point -----------------------------------------------------------------
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) cur.s[r] = s[r];
-    eval_point(cur, true);
-    for (int k = 0; k < 6; ++k) cres[k] = cur.c[k];
-#pragma unroll
-    for (int r = 0; r < kNumRows; ++r) rd[r] = cur.rd[r];
-    fval = cur.f;
-    bool cur_finite = cur.finite;
-    const double theta0 = cur.theta;
-    const double theta_max = o.theta_max_fact * fmax(1.0, theta0);
-    const double theta_min = o.theta_min_fact * fmax(1.0, theta0);
-    double dw_last = 0.0;
-    int acc_count = 0;
+
+    // ---- phase-loop state ------------------------------------------------------------
+    int phase = kPhInit;
     int status = kMaxIterExceeded;
-    int it = 0;
-    const double mu_floor =
-        fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol * df) / (o.barrier_tol_factor + 1.0));
-    double last_alpha = 0.0, last_dw = 0.0;
+    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0;
+    bool cur_finite = true, soc_done = false, f_type = false;
+    double theta_max = 0.0, theta_min = 0.0, mu_floor = 0.0;
+    double dw = 0.0, dw_last = 0.0, last_alpha = 0.0, last_dw = 0.0;
+    double alpha = 0.0, a_soc = 0.0, amin = 0.0, gpd = 0.0, theta = 0.0, phi = 0.0, th_old = 0.0;
+    double c_soc[6], d_soc[kNumRows];
+    // plain (non-SOC) step saved while a second-order correction is being tried
+    double sv_dx[6], sv_dsh = 0.0, sv_du[2] = {0.0, 0.0}, sv_dsr[kNumRows], sv_lam[6], sv_y0[7];
+    double zero_rows[kNumRows], zero6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int r = 0; r < kNumRows; ++r) { zero_rows[r] = 0.0; d_soc[r] = 0.0; sv_dsr[r] = 0.0; }
+    for (int a = 0; a < 6; ++a) { c_soc[a] = 0.0; sv_dx[a] = 0.0; sv_lam[a] = 0.0; }
+    for (int a = 0; a < 7; ++a) sv_y0[a] = 0.0;
+    Point tp;
 
     while (true) {
-      eval_derivs(0);
-      if (!cur_finite) { status = kInvalidNumber; break; }
-      // ---- convergence tests -----------------------------------------------------------
-      Errors e0 = compute_errors(0.0);
-      const double viol = orig_violation();
-      if (out.trace && lane == 0) {
-        double* tr = out.trace + (size_t)it * kTraceCols;
-        tr[0] = fval / df; tr[1] = e0.E; tr[2] = e0.pr_inf; tr[3] = e0.dual_inf;
-        tr[4] = e0.compl_inf; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
-      }
-      if (!finite_d(e0.E)) { status = kInvalidNumber; break; }
-      if (e0.E <= o.tol && e0.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
-          e0.compl_inf / df <= o.compl_inf_tol) {
-        status = kSolveSucceeded;
-        break;
-      }
-      if (e0.E <= o.acceptable_tol && e0.dual_inf / df <= o.acceptable_dual_inf_tol &&
-          viol <= o.acceptable_constr_viol_tol &&
-          e0.compl_inf / df <= o.acceptable_compl_inf_tol) {
-        acc_count++;
-        if (acc_count >= o.acceptable_iter) { status = kSolvedToAcceptableLevel; break; }
-      } else {
-        acc_count = 0;
-      }
-      if (it >= o.max_iter) { status = kMaxIterExceeded; break; }
-      // ---- barrier parameter update (monotone) ---------------------------------------
-      while (true) {
-        Errors em = compute_errors(mu);
-        if (em.E <= o.barrier_tol_factor * mu && mu > mu_floor) {
-          mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
-                                   pow(mu, o.mu_superlinear_decrease_power)));
-          tau = fmax(o.tau_min, 1.0 - mu);
-          filt_n = 0;
-        } else {
-          break;
-        }
-      }
-      // ---- search direction with inertia correction ----------------------------------
-      double dw = 0.0;
-      bool first_try = true, failed = false;
-      while (true) {
-        write_row_terms(0, dw, rd, cres);
-        syncwarp();
-        if (kkt_solve(dw)) break;
-        if (first_try) {
-          dw = (dw_last == 0.0) ? o.delta_w_init : fmax(o.delta_w_min, dw_last * o.kappa_w_minus);
-          first_try = false;
-        } else {
-          dw *= (dw_last == 0.0 || 1.0e5 * dw_last < dw) ? o.kappa_w_plus_first : o.kappa_w_plus;
-        }
-        if (dw > o.delta_w_max) { failed = true; break; }
-      }
-      if (failed) { status = kErrorInStepComputation; break; }
-      if (dw > 0.0) dw_last = dw;
-      last_dw = dw;
-      // ---- slack / multiplier steps ---------------------------------------------------
-      double dsr[kNumRows];
-      slack_steps(rd, dsr);
-      double alpha_max = ftb_primal(dsr);
-      // grad(phi)' d
-      double gpd = 0.0;
-      {
-        const double dup1 = shfl(du[1], prev_lane());
-        if (act) {
-          gpd = gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
-                gcost[4] * dx[4];
-          // steer-rate cost: 2 beta df (sig_k - sig_{k-1}) (dsig_k - dsig_{k-1})
-          if (lane >= 1) gpd += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
-#pragma unroll
-          for (int r = 0; r < kNumRows; ++r)
-            if (on(r)) gpd += gsb_row(r) * dsr[r];
-        }
-      }
-      gpd = warp_sum(gpd);
-      const double theta = warp_sum(theta_local());
-      const double phi = fval + warp_sum(act ? barrier_terms(s) : 0.0);
-      double amin;
-      if (gpd < 0.0) {
-        amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
-        if (theta <= theta_min)
-          amin = fmin(amin, o.delta * pow(theta, o.s_theta) / pow(-gpd, o.s_phi));
-      } else {
-        amin = o.gamma_theta;
-      }
-      amin *= o.alpha_min_frac;
-      // ---- filter line search ------------------------------------------------------------
-      double alpha = alpha_max;
-      bool accepted = false, f_type = false, soc_done = false;
-      int n_ls = 0;
-      Point tp;
-      double acc_newlam[6], acc_newy0[7];
-      for (int a = 0; a < 6; ++a) acc_newlam[a] = newlam[a];
-      for (int a = 0; a < 7; ++a) acc_newy0[a] = newy0[a];
-      double acc_dsr[kNumRows];
-#pragma unroll
-      for (int r = 0; r < kNumRows; ++r) acc_dsr[r] = dsr[r];
-      const bool sw_base = gpd < 0.0;
-      while ((alpha >= amin || n_ls == 0) && n_ls < 60) {
-        for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + alpha * dx[a];
-        tp.sh = sh + alpha * dsh;
-        tp.u[0] = u[0] + alpha * du[0];
-        tp.u[1] = u[1] + alpha * du[1];
-#pragma unroll
-        for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + alpha * dsr[r];
-        eval_point(tp, true);
-        n_ls++;
-        bool ok = tp.finite && tp.theta <= theta_max;
-        if (ok) {
-          const bool switching =
-              sw_base && alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
-          if (theta <= theta_min && switching) {
-            ok = cmp_le(tp.phi - phi, o.eta_phi * alpha * gpd, phi);
-            f_type = true;
-          } else {
-            ok = cmp_le(tp.theta, (1.0 - o.gamma_theta) * theta, theta) ||
-                 cmp_le(tp.phi - phi, -o.gamma_phi * theta, phi);
-            f_type = false;
+      // ================= A. derivatives, convergence tests, barrier update ===============
+      if (phase == kPhInit || phase == kPhNewton) {
+        eval_derivs(phase == kPhInit ? 1 : 0);
+        if (phase == kPhInit) {
+          // ---- gradient-based scaling at the starting point ----------------------------
+          double sig_n_raw = shfl(sigc_prev, next_lane());
+          double sig_n = (lane == N - 1) ? 0.0 : sig_n_raw;
+          double g = 0.0;
+          if (act) {
+            for (int k = 0; k < 5; ++k) g = fmax(g, fabs(gcost[k]));
+            g = fmax(g, fabs(2.0 * p.beta_delta * (sigc_prev - sig_n)));
           }
-          if (ok) ok = filter_ok(tp.theta, tp.phi);
-        }
-        if (ok) { accepted = true; break; }
-        // ---- second-order correction on the first trial step ---------------------------
-        if (!soc_done && n_ls == 1 && tp.finite && tp.theta >= theta) {
-          soc_done = true;
-          double c_soc[6], d_soc[kNumRows];
-          for (int a = 0; a < 6; ++a) c_soc[a] = alpha * cres[a] + tp.c[a];
-#pragma unroll
-          for (int r = 0; r < kNumRows; ++r) d_soc[r] = alpha * rd[r] + tp.rd[r];
-          double th_old = theta;
-          // keep the plain step to restore if no SOC step is accepted
-          double dx0[6], dsh0 = dsh, du0[2] = {du[0], du[1]};
-          for (int a = 0; a < 6; ++a) dx0[a] = dx[a];
-          for (int isoc = 0; isoc < o.max_soc; ++isoc) {
-            write_row_terms(0, dw, d_soc, c_soc);
-            syncwarp();
-            if (!kkt_solve(dw)) break;
-            double dss[kNumRows];
-            slack_steps(d_soc, dss);
-            const double a_soc = ftb_primal(dss);
-            for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + a_soc * dx[a];
-            tp.sh = sh + a_soc * dsh;
-            tp.u[0] = u[0] + a_soc * du[0];
-            tp.u[1] = u[1] + a_soc * du[1];
-#pragma unroll
-            for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + a_soc * dss[r];
-            eval_point(tp, true);
-            if (!tp.finite || tp.theta > theta_max) break;
-            const bool switching =
-                sw_base && alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
-            bool ok2;
-            if (theta <= theta_min && switching) {
-              ok2 = cmp_le(tp.phi - phi, o.eta_phi * alpha * gpd, phi);
-              f_type = true;
+          g = warp_max(g);
+          if (g > o.nlp_scaling_max_gradient)
+            df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
+          double rm[6];
+          rm[0] = fmax(1.0, fmax(fabs(lin.aX[0]), fmax(fabs(lin.aX[1]), fabs(lin.aX[2]))));
+          rm[1] = fmax(1.0, fmax(fabs(lin.aY[0]), fmax(fabs(lin.aY[1]), fabs(lin.aY[2]))));
+          rm[2] = fmax(1.0, fabs(cfg.Ts));
+          for (int i = 0; i < 3; ++i) {
+            double m = 1.0;
+            for (int k = 0; k < 3; ++k) m = fmax(m, fabs(lin.d[i][k]));
+            for (int k = 0; k < 2; ++k) m = fmax(m, fabs(lin.bu[i][k]));
+            rm[3 + i] = m;
+          }
+          for (int k = 0; k < 6; ++k)
+            dcs[k] = (rm[k] > o.nlp_scaling_max_gradient)
+                         ? fmax(o.nlp_scaling_max_gradient / rm[k], o.nlp_scaling_min_value) : 1.0;
+          double gl = fmax(fabs(gC[0]), fmax(fabs(gC[1]), fabs(gC[2])));
+          if (cfg.lane_con && gl > o.nlp_scaling_max_gradient)
+            ddl = fmax(o.nlp_scaling_max_gradient / gl, o.nlp_scaling_min_value);
+          // the lane-row scale is made uniform over the warp (its bounds live in shared memory)
+          ddl = warp_min(act ? ddl : 1.0);
+          for (int k = 0; k < 5; ++k) gcost[k] *= df;    // eval_derivs ran with df = ddl = 1
+          for (int k = 0; k < 3; ++k) gC[k] *= ddl;
+          mu_floor = fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol * df) / (o.barrier_tol_factor + 1.0));
+          // ---- relaxed bounds ------------------------------------------------------------
+          if (lane < kNumRows) {
+            double l, h;
+            row_bounds(lane, l, h);
+            if (lane == kLane) { l *= ddl; h *= ddl; }
+            if (row_hasL(lane)) l -= fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(l)));
+            else l = -inf;
+            if (row_hasU(lane)) h += fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(h)));
+            else h = inf;
+            ws.misc[lane] = l;
+            ws.misc[kNumRows + lane] = h;
+          }
+          syncwarp();
+        } else {
+          if (!cur_finite) { status = kInvalidNumber; break; }
+          bool done = false;
+#pragma unroll 1
+          for (int pass = 0;; ++pass) {
+            Errors e = compute_errors(pass == 0 ? 0.0 : mu);
+            if (pass == 0) {
+              const double viol = orig_violation();
+              if (out.trace && lane == 0) {
+                double* tr = out.trace + (size_t)it * kTraceCols;
+                tr[0] = fval / df; tr[1] = e.E; tr[2] = e.pr_inf; tr[3] = e.dual_inf;
+                tr[4] = e.compl_inf; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
+              }
+              if (!finite_d(e.E)) { status = kInvalidNumber; done = true; break; }
+              if (e.E <= o.tol && e.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
+                  e.compl_inf / df <= o.compl_inf_tol) {
+                status = kSolveSucceeded;
+                done = true;
+                break;
+              }
+              if (e.E <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
+                  viol <= o.acceptable_constr_viol_tol &&
+                  e.compl_inf / df <= o.acceptable_compl_inf_tol) {
+                acc_count++;
+                if (acc_count >= o.acceptable_iter) {
+                  status = kSolvedToAcceptableLevel;
+                  done = true;
+                  break;
+                }
+              } else {
+                acc_count = 0;
+              }
+              if (it >= o.max_iter) { status = kMaxIterExceeded; done = true; break; }
             } else {
-              ok2 = cmp_le(tp.theta, (1.0 - o.gamma_theta) * theta, theta) ||
-                    cmp_le(tp.phi - phi, -o.gamma_phi * theta, phi);
-              f_type = false;
+              // monotone barrier update (Waechter & Biegler eq. (7))
+              if (e.E <= o.barrier_tol_factor * mu && mu > mu_floor) {
+                mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
+                                         pow(mu, o.mu_superlinear_decrease_power)));
+                tau = fmax(o.tau_min, 1.0 - mu);
+                filt_n = 0;
+              } else {
+                break;
+              }
             }
-            if (ok2 && filter_ok(tp.theta, tp.phi)) {
-              accepted = true;
-              alpha = a_soc;
-              for (int a = 0; a < 6; ++a) acc_newlam[a] = newlam[a];
-              for (int a = 0; a < 7; ++a) acc_newy0[a] = newy0[a];
-#pragma unroll
-              for (int r = 0; r < kNumRows; ++r) acc_dsr[r] = dss[r];
-              break;
+          }
+          if (done) break;
+          dw = 0.0;
+        }
+      }
+      // ================= B. linear solve (single call site) ===================================
+      if (phase == kPhInit || phase == kPhNewton || phase == kPhSoc) {
+        const int mode = (phase == kPhInit) ? 1 : 0;
+        const double* rdv = (phase == kPhInit) ? zero_rows : ((phase == kPhSoc) ? d_soc : rd);
+        const double* cv = (phase == kPhInit) ? zero6 : ((phase == kPhSoc) ? c_soc : cres);
+        double dwu = (phase == kPhInit) ? 1.0 : dw;
+        bool first_try = true, ok = false, failed = false;
+#pragma unroll 1
+        while (true) {
+          write_row_terms(mode, dwu, rdv, cv);
+          syncwarp();
+          ok = kkt_solve(dwu);
+          if (ok || phase != kPhNewton) break;
+          // inertia correction (IPOPT's PDPerturbationHandler schedule)
+          if (first_try) {
+            dw = (dw_last == 0.0) ? o.delta_w_init : fmax(o.delta_w_min, dw_last * o.kappa_w_minus);
+            first_try = false;
+          } else {
+            dw *= (dw_last == 0.0 || 1.0e5 * dw_last < dw) ? o.kappa_w_plus_first : o.kappa_w_plus;
+          }
+          if (dw > o.delta_w_max) { failed = true; break; }
+          dwu = dw;
+        }
+        if (failed) { status = kErrorInStepComputation; break; }
+        const double a_new = slack_steps(rdv);     // dsr = J_d dx + rdv ; FTB step
+        if (phase == kPhInit) {
+          // ---- least-squares multipliers: y = -(QP multipliers), yd = (vU - vL) - J_d dx ----
+          double ymax = 0.0;
+          if (ok && act)
+            for (int a = 0; a < 6; ++a) { lam[a] = -newlam[a]; ymax = fmax(ymax, fabs(lam[a] / dcs[a])); }
+#pragma unroll 1
+          for (int r = 0; r < kNumRows; ++r) {
+            if (!on(r) || !ok) continue;
+            yd[r] = ((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0)) - dsr[r];
+            ymax = fmax(ymax, fabs(yd[r]));
+          }
+          for (int a = 0; a < 7; ++a) { y0[a] = ok ? -newy0[a] : 0.0; ymax = fmax(ymax, fabs(y0[a])); }
+          ymax = warp_max(ymax);
+          if (!ok || !(ymax <= o.constr_mult_init_max)) {
+            for (int a = 0; a < 6; ++a) lam[a] = 0.0;
+            for (int a = 0; a < 7; ++a) y0[a] = 0.0;
+#pragma unroll 1
+            for (int r = 0; r < kNumRows; ++r) yd[r] = 0.0;
+          }
+          for (int a = 0; a < 6; ++a) dx[a] = 0.0;     // the init phases evaluate the point itself
+          dsh = 0.0;
+          du[0] = du[1] = 0.0;
+#pragma unroll 1
+          for (int r = 0; r < kNumRows; ++r) dsr[r] = 0.0;
+          alpha = 0.0;
+        } else if (phase == kPhNewton) {
+          if (dw > 0.0) dw_last = dw;
+          last_dw = dw;
+          alpha = a_new;
+          // grad(phi)' d
+          double g = 0.0;
+          {
+            const double dup1 = shfl(du[1], prev_lane());
+            if (act) {
+              g = gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
+                  gcost[4] * dx[4];
+              if (lane >= 1) g += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
             }
-            if (tp.theta > o.kappa_soc * th_old) break;
+#pragma unroll 1
+            for (int r = 0; r < kNumRows; ++r) {
+              if (!on(r)) continue;
+              double sg, gb;
+              sigma_gsb(r, sg, gb);
+              g += gb * dsr[r];
+            }
+          }
+          gpd = warp_sum(g);
+          theta = warp_sum(theta_local());
+          phi = fval + mu * barB;
+          if (gpd < 0.0) {
+            amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
+            if (theta <= theta_min)
+              amin = fmin(amin, o.delta * pow(theta, o.s_theta) / pow(-gpd, o.s_phi));
+          } else {
+            amin = o.gamma_theta;
+          }
+          amin *= o.alpha_min_frac;
+          n_ls = 0;
+          soc_done = false;
+        } else {   // kPhSoc
+          if (!ok) {
+            // abandon the correction: restore the plain step and keep backtracking
+            for (int a = 0; a < 6; ++a) { dx[a] = sv_dx[a]; newlam[a] = sv_lam[a]; }
+            for (int a = 0; a < 7; ++a) newy0[a] = sv_y0[a];
+            dsh = sv_dsh;
+            du[0] = sv_du[0];
+            du[1] = sv_du[1];
+#pragma unroll 1
+            for (int r = 0; r < kNumRows; ++r) dsr[r] = sv_dsr[r];
+            alpha *= o.alpha_red_factor;
+            phase = kPhBacktrack;
+            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+          } else {
+            a_soc = a_new;
+          }
+        }
+      }
+      // ================= C. trial point (single call site) =======================================
+      {
+        const double at = (phase == kPhSoc) ? a_soc : alpha;
+        for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + at * dx[a];
+        tp.sh = sh + at * dsh;
+        tp.u[0] = u[0] + at * du[0];
+        tp.u[1] = u[1] + at * du[1];
+#pragma unroll 1
+        for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + at * dsr[r];
+        eval_point(tp);
+      }
+      // ================= D. decisions ===========================================================
+      if (phase == kPhInit) {
+        // slacks pushed into their (relaxed) bounds; tp.rd holds the row values (s was 0)
+#pragma unroll 1
+        for (int r = 0; r < kNumRows; ++r) {
+          if (!on(r)) { s[r] = 0.0; continue; }
+          double v = tp.rd[r];
+          const double l = lo(r), h = hi(r);
+          double pl, pu;
+          if (row_hasL(r) && row_hasU(r)) {
+            pl = fmin(o.bound_push * fmax(1.0, fabs(l)), o.bound_frac * (h - l));
+            pu = fmin(o.bound_push * fmax(1.0, fabs(h)), o.bound_frac * (h - l));
+          } else {
+            pl = o.bound_push * fmax(1.0, fabs(l));
+            pu = o.bound_push * fmax(1.0, fabs(h));
+          }
+          if (row_hasL(r)) v = fmax(v, l + pl);
+          if (row_hasU(r)) v = fmin(v, h - pu);
+          s[r] = v;
+        }
+        phase = kPhInit2;
+        continue;
+      }
+      if (phase == kPhInit2) {
+        for (int k = 0; k < 6; ++k) cres[k] = tp.c[k];
+#pragma unroll 1
+        for (int r = 0; r < kNumRows; ++r) rd[r] = tp.rd[r];
+        fval = tp.f;
+        barB = tp.barB;
+        cur_finite = tp.finite;
+        theta_max = o.theta_max_fact * fmax(1.0, tp.theta);
+        theta_min = o.theta_min_fact * fmax(1.0, tp.theta);
+        phase = kPhNewton;
+        continue;
+      }
+      // ---- acceptance test of the trial point (plain or SOC step) --------------------------------
+      n_ls += (phase == kPhSoc) ? 0 : 1;
+      const double tphi = tp.f + mu * tp.barB;
+      bool ok = tp.finite && tp.theta <= theta_max;
+      if (ok) {
+        const bool switching = gpd < 0.0 &&
+            alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
+        if (theta <= theta_min && switching) {
+          ok = cmp_le(tphi - phi, o.eta_phi * alpha * gpd, phi);
+          f_type = true;
+        } else {
+          ok = cmp_le(tp.theta, (1.0 - o.gamma_theta) * theta, theta) ||
+               cmp_le(tphi - phi, -o.gamma_phi * theta, phi);
+          f_type = false;
+        }
+        if (ok) ok = filter_ok(tp.theta, tphi);
+      }
+      if (!ok) {
+        if (phase == kPhSoc) {
+          soc_count++;
+          if (!tp.finite || tp.theta > theta_max || tp.theta > o.kappa_soc * th_old ||
+              soc_count >= o.max_soc) {
+            // correction failed: back to the plain step, shorten it
+            for (int a = 0; a < 6; ++a) { dx[a] = sv_dx[a]; newlam[a] = sv_lam[a]; }
+            for (int a = 0; a < 7; ++a) newy0[a] = sv_y0[a];
+            dsh = sv_dsh;
+            du[0] = sv_du[0];
+            du[1] = sv_du[1];
+#pragma unroll 1
+            for (int r = 0; r < kNumRows; ++r) dsr[r] = sv_dsr[r];
+            alpha *= o.alpha_red_factor;
+            phase = kPhBacktrack;
+            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+          } else {
             th_old = tp.theta;
             for (int a = 0; a < 6; ++a) c_soc[a] = a_soc * c_soc[a] + tp.c[a];
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < kNumRows; ++r) d_soc[r] = a_soc * d_soc[r] + tp.rd[r];
           }
-          if (accepted) break;
-          for (int a = 0; a < 6; ++a) dx[a] = dx0[a];
-          dsh = dsh0;
-          du[0] = du0[0];
-          du[1] = du0[1];
+          continue;
+        }
+        // plain step rejected: second-order correction on the first trial, else backtrack
+        if (!soc_done && n_ls == 1 && tp.finite && tp.theta >= theta && o.max_soc > 0) {
+          soc_done = true;
+          soc_count = 0;
+          th_old = theta;
+          for (int a = 0; a < 6; ++a) {
+            c_soc[a] = alpha * cres[a] + tp.c[a];
+            sv_dx[a] = dx[a];
+            sv_lam[a] = newlam[a];
+          }
+          for (int a = 0; a < 7; ++a) sv_y0[a] = newy0[a];
+          sv_dsh = dsh;
+          sv_du[0] = du[0];
+          sv_du[1] = du[1];
+#pragma unroll 1
+          for (int r = 0; r < kNumRows; ++r) {
+            d_soc[r] = alpha * rd[r] + tp.rd[r];
+            sv_dsr[r] = dsr[r];
+          }
+          phase = kPhSoc;
+          continue;
         }
         alpha *= o.alpha_red_factor;
+        phase = kPhBacktrack;
+        if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+        continue;
       }
-      if (!accepted) { status = kRestorationNeeded; break; }
+      // ================= E. accept the trial point ===============================================
       if (!f_type) filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);
-      // ---- dual steps --------------------------------------------------------------------
-      // dyd = D ds + gsb - yd (with the ds of the accepted direction; for SOC its own rhs)
+      const double astep = (phase == kPhSoc) ? a_soc : alpha;
+      // dual steps: dyd = D ds + gsb - yd ; dv from the linearised complementarity
       double az = 1.0;
-      double dvL[kNumRows], dvU[kNumRows], dyd[kNumRows];
-#pragma unroll
+      double dvL[kNumRows], dvU[kNumRows];
+#pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
-        dvL[r] = dvU[r] = dyd[r] = 0.0;
-        if (!on(r)) continue;
-        const double D = sigma_row(r) + dw;
-        dyd[r] = D * acc_dsr[r] + gsb_row(r) - yd[r];
-        if (row_hasL(r)) {
-          const double sl = s[r] - lo(r);
-          dvL[r] = mu / sl - vL[r] - vL[r] / sl * acc_dsr[r];
-          if (dvL[r] < 0.0) az = fmin(az, -tau * vL[r] / dvL[r]);
+        double a = 0.0, b = 0.0;
+        if (on(r)) {
+          double sg, gb;
+          sigma_gsb(r, sg, gb);
+          const double dyd = (sg + dw) * dsr[r] + gb - yd[r];
+          yd[r] += astep * dyd;
+          if (row_hasL(r)) {
+            const double sl = s[r] - lo(r);
+            a = mu / sl - vL[r] - vL[r] / sl * dsr[r];
+            if (a < 0.0) az = fmin(az, -tau * vL[r] / a);
+          }
+          if (row_hasU(r)) {
+            const double su = hi(r) - s[r];
+            b = mu / su - vU[r] + vU[r] / su * dsr[r];
+            if (b < 0.0) az = fmin(az, -tau * vU[r] / b);
+          }
         }
-        if (row_hasU(r)) {
-          const double su = hi(r) - s[r];
-          dvU[r] = mu / su - vU[r] + vU[r] / su * acc_dsr[r];
-          if (dvU[r] < 0.0) az = fmin(az, -tau * vU[r] / dvU[r]);
-        }
+        dvL[r] = a;
+        dvU[r] = b;
       }
       az = warp_min(az);
-      // ---- accept -------------------------------------------------------------------------
       for (int a = 0; a < 6; ++a) {
         x[a] = tp.x[a];
         cres[a] = tp.c[a];
-        if (act) lam[a] += alpha * (acc_newlam[a] - lam[a]);
+        if (act) lam[a] += astep * (newlam[a] - lam[a]);
       }
-      for (int a = 0; a < 7; ++a) y0[a] += alpha * (acc_newy0[a] - y0[a]);
+      for (int a = 0; a < 7; ++a) y0[a] += astep * (newy0[a] - y0[a]);
       sh = tp.sh;
       u[0] = tp.u[0];
       u[1] = tp.u[1];
       fval = tp.f;
+      barB = tp.barB;
       cur_finite = tp.finite;
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
         if (!on(r)) continue;
         s[r] = tp.s[r];
         rd[r] = tp.rd[r];
-        yd[r] += alpha * dyd[r];
         if (row_hasL(r)) {
           const double sl = s[r] - lo(r);
           double v = vL[r] + az * dvL[r];
@@ -1406,23 +1433,26 @@ struct WarpSolver {
           vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
         }
       }
-      last_alpha = alpha;
+      last_alpha = astep;
       it++;
+      phase = kPhNewton;
     }
 
     // ---- outputs ---------------------------------------------------------------------------
     {
       double xp[6], shp, up[2];
       gather_prev(x, sh, u, xp, shp, up);
-      StageCost sc;
-      stage_cost(p, pb.cx, pb.cy, xp, shp, 0, sc);
+      Poly4 px, py;
+      poly4_eval(pb.cx, shp, 1, px);
+      poly4_eval(pb.cy, shp, 1, py);
+      const double dX = xp[0] - px.p, dY = xp[1] - py.p;
       if (act) {
         out.U[lane] = u[0];
         out.U[N + lane] = u[1];
         for (int a = 0; a < 6; ++a) out.X[a * (N + 1) + lane + 1] = x[a];
         out.S[lane + 1] = sh;
-        out.eC[lane] = sc.eC;       // e_hat_C(S_hat[i], States[:, i]), i = 0..N-1
-        out.eL[lane] = sc.eL;
+        out.eC[lane] = py.d1 * dX - px.d1 * dY;      // e_hat_C(S_hat[i], States[:, i]), i < N
+        out.eL[lane] = -px.d1 * dX - py.d1 * dY;
       }
       if (lane == 0) {
         for (int a = 0; a < 6; ++a) out.X[a * (N + 1)] = pb.x0[a];
@@ -1463,7 +1493,6 @@ struct WarpSolver {
   }
 };
 
-
 // ---------------------------------------------------------------------------
 // One problem of a batch: load inputs, run the solver, store the outputs.
 // Called by every lane of a warp with the same arguments.
@@ -1472,8 +1501,9 @@ MPCR_HD int lam_g_stride(const Config& c) {
   return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
 }
 
+template <int MODEL>
 MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
-                          int trace_rows, double* wsbase) {
+                          int trace_rows, double* wsbase, double* stagebase) {
   const int N = cfg.N;
   ProblemView pv;
   for (int k = 0; k < 6; ++k) pv.x0[k] = in.x0[(size_t)b * 6 + k];
@@ -1512,8 +1542,15 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     for (int k = lane_id(); k < ls; k += 32) so.lam_g[k] = 0.0;
     syncwarp();
   }
-  WarpSolver solver(cfg, prm, pv, wsbase);
+  WarpSolver<MODEL> solver(cfg, prm, pv, wsbase, stagebase);
   solver.solve(so);
+}
+
+MPCR_D void solve_problem_any(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
+                              int trace_rows, double* wsbase, double* stagebase) {
+  if (cfg.model == kDynamic) solve_problem<kDynamic>(cfg, in, out, b, trace_rows, wsbase, stagebase);
+  else if (cfg.model == kKinematic) solve_problem<kKinematic>(cfg, in, out, b, trace_rows, wsbase, stagebase);
+  else solve_problem<kBlended>(cfg, in, out, b, trace_rows, wsbase, stagebase);
 }
 
 }  // namespace mpcr

@@ -19,7 +19,7 @@ struct Job {
 };
 void lane_body(void* p) {
   Job* j = (Job*)p;
-  mpcr::solve_problem(*j->cfg, *j->in, *j->out, j->b, j->trace_rows, j->ws);
+  mpcr::solve_problem_any(*j->cfg, *j->in, *j->out, j->b, j->trace_rows, j->ws, nullptr);
 }
 }  // namespace
 

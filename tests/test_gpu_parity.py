@@ -102,7 +102,10 @@ def test_full_size_properties(cfg2, solver):
     U, X, S = r.U[conv], r.X[conv], r.S[conv]
     # dynamics residual of the returned trajectory (explicit Euler, control/MPC.py:186-229)
     f = V.f_dynamic(np.moveaxis(X[:, :, :-1], 1, 2), np.moveaxis(U, 1, 2), 0.05)
-    assert np.abs(np.moveaxis(X[:, :, 1:], 1, 2) - f).max() <= 1e-4 * 1.01
+    resid = np.abs(np.moveaxis(X[:, :, 1:], 1, 2) - f).reshape(len(X), -1).max(axis=1)
+    st = r.status[conv]
+    assert resid[st == 0].max() <= 1e-4 * 1.01        # constr_viol_tol
+    assert resid.max() <= 1e-2 * 1.01                 # acceptable_constr_viol_tol (status 1)
     # bounds (relaxed by IPOPT's 1e-8) and rate rows, incl. the wrap rows
     assert U[:, 0].max() <= 0.85 + 1e-6 and U[:, 0].min() >= -1 - 1e-6
     assert np.abs(U[:, 1]).max() <= 0.9 + 1e-6
