@@ -68,11 +68,12 @@ MPCR_D bool finite_d(double v) { return v == v && fabs(v) < 1.0e300; }
 constexpr int kOffA = 0;        // StageLin (21)
 constexpr int kOffB = 21;       // b = -c_{k+1}  (6)
 constexpr int kOffHs = 27;      // packed sparse stage Hessian (32)
-constexpr int kOffGs = 59;      // dense stage gradient over (z, w) (12)
-constexpr int kOffK = 71;       // feedback gain (3 x 9)
+constexpr int kOffGs = 59;      // dense stage gradient over (z, w) (12); gs[2] is always 0
+constexpr int kZeroSlot = 34;   // = kOffGs + 2 relative to kOffHs: the always-zero slot
+constexpr int kOffK = 71;       // feedback gain (3 x 9); reused for the forward-sweep results
 constexpr int kOffKf = 98;      // feed-forward, 3 right-hand sides (3 x 3)
-constexpr int kOffRow = 107;    // row terms: R_tt, R_ss, D_lane, gC[3] (6)
-constexpr int kStride = 113;    // odd: conflict-free lane-parallel writes
+constexpr int kOffBase = 107;   // derivative part of (thr,thr), (st,st) (these also carry row terms)
+constexpr int kStride = 109;    // odd: conflict-free lane-parallel writes
 constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
 
 constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
@@ -223,7 +224,8 @@ struct WarpSolver {
   // filter: one entry per lane
   double filt_th, filt_ph;
   int filt_n;
-  int gslot[5];
+  int colslot[12];          // packed slot of stage-Hessian entry (r, lane) for lanes 0..11
+  double dwflag;            // 1 if diagonal entry (lane, lane) receives delta_w
 
   MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, double* wsbase,
                     double* stagebase)
@@ -232,12 +234,8 @@ struct WarpSolver {
     N = c.N;
     act = lane < N;
     ws.bind(wsbase, stagebase, N);
-    for (int j = 0; j < 5; ++j) {
-      int e = lane + 32 * j;
-      int slot = 0xff;
-      if (e < 144) slot = slot_of(e / 12, e % 12);
-      gslot[j] = slot;
-    }
+    for (int r = 0; r < 12; ++r) colslot[r] = (lane < 12) ? (slot_of(r, lane) & 0xff) : kZeroSlot;
+    dwflag = (lane <= 6 || lane == 9 || lane == 10) ? 1.0 : 0.0;
   }
 
   MPCR_D bool on(int r) const { return (rowmask >> r) & 1u; }
@@ -306,13 +304,14 @@ struct WarpSolver {
   // objective / constraints at a point (line search trial or current iterate)
   // -------------------------------------------------------------------------
   struct Point {
-    double x[6], sh, u[2], s[kNumRows];
+    double x[6], sh, u[2];
     double c[6], rd[kNumRows];
     double f, theta, barB;  // uniform
     bool finite;            // uniform
   };
 
-  MPCR_D void eval_point(Point& t) const {
+  // slacks of the point are s + at * dsr (not stored)
+  MPCR_D void eval_point(Point& t, double at) const {
     double xp[6], shp, up[2];
     gather_prev(t.x, t.sh, t.u, xp, shp, up);
     double f[6];
@@ -339,7 +338,7 @@ struct WarpSolver {
     for (int r = 0; r < kNumRows; ++r) {
       double rdv = 0.0;
       if (on(r)) {
-        const double sv = t.s[r];
+        const double sv = s[r] + at * dsr[r];
         rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
         th += fabs(rdv);
         if (row_hasL(r)) {
@@ -373,6 +372,7 @@ struct WarpSolver {
   double gcost[5];        // df * grad cost of state lane+1 over (X, Y, s, vx, vy) (incl -lambda_s)
   double gC[3];           // ddl * grad e_C over (X, Y, s) at state lane+1 (lane row)
   double sigc_prev;       // sigma_k - sigma_{k-1} (0 for lane 0)
+  double hcp6[6];         // df * cost Hessian over (X, Y, s) of state `lane` (+ lane-row curvature)
 
   MPCR_D void eval_derivs(int mode) {
     double xp[6], shp, up[2];
@@ -417,19 +417,23 @@ struct WarpSolver {
       for (int i = 0; i < 3; ++i)
         for (int k = 0; k < 2; ++k) st[kOffA + 15 + 2 * i + k] = lin.bu[i][k];
       double* hs = st + kOffHs;
-      for (int k = 0; k < 6; ++k) hs[k] = hcp[k];
+      double* base = st + kOffBase;
+      // (thr,thr), (st,st) also receive row terms: their derivative part is kept in `base`;
+      // the (X,Y,s) block's derivative part stays in registers (hcp6)
+      for (int k = 0; k < 6; ++k) hcp6[k] = hcp[k];
       for (int k = 0; k < kHmDoubles; ++k) hs[6 + k] = (mode == 0) ? -hm[k] : 0.0;
       hs[6 + hm_idx(1, 1)] += hcp[6];
       hs[6 + hm_idx(2, 2)] += hcp[7];
+      base[0] = hs[6 + hm_idx(4, 4)];
+      base[1] = hs[6 + hm_idx(5, 5)];
       if (lane == N - 1) {
         double* hN = ws.st(N) + kOffHs;
-        for (int k = 0; k < 6; ++k) hN[k] = hc[k];
+        double* bN = ws.st(N) + kOffK;          // the terminal stage has no gain: free space
+        for (int k = 0; k < 6; ++k) bN[k] = hc[k];
         for (int k = 0; k < kHmDoubles; ++k) hN[6 + k] = 0.0;
         hN[6 + hm_idx(1, 1)] = hc[6];
         hN[6 + hm_idx(2, 2)] = hc[7];
         for (int k = 27; k < 32; ++k) hN[k] = 0.0;
-        ws.st(N)[kOffRow + 0] = 0.0;
-        ws.st(N)[kOffRow + 1] = 0.0;
       }
     }
   }
@@ -460,9 +464,13 @@ struct WarpSolver {
     }
   }
 
+  // rdv / cv may be null (= zero right-hand sides)
   MPCR_D void write_row_terms(int mode, double dw, const double* rdv /* [kNumRows] */,
                               const double* cv /* [6] dynamics rhs */) {
-    double D[kNumRows], e[kNumRows];
+    // D and e of the individual rows, accumulated by role (no per-row arrays)
+    double Rtt = 0.0, Rss = 0.0, eth = 0.0, est = 0.0;     // rows acting on (thr_k, st_k) alone
+    double Dthr = 0.0, ethr = 0.0, Dst = 0.0, esr = 0.0;   // rate rows (kDThr, kDSt)
+    double Dprog = 0.0, eprog = 0.0, Dlane = 0.0, elane = 0.0;
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
       double Dr = 0.0, er = 0.0;
@@ -471,18 +479,24 @@ struct WarpSolver {
           double sg, g;
           sigma_gsb(r, sg, g);
           Dr = sg + dw;
-          er = Dr * rdv[r] + g;
+          er = Dr * (rdv ? rdv[r] : 0.0) + g;
         } else {
           Dr = 1.0;
           er = -((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0));
         }
       }
-      D[r] = Dr;
-      e[r] = er;
+      switch (r) {
+        case kThrUb: case kThrLb: case kDThr0: Rtt += Dr; eth += er; break;
+        case kStUb: case kStLb: case kDSt0: Rss += Dr; est += er; break;
+        case kDThr: Dthr = Dr; ethr = er; break;
+        case kDSt: Dst = Dr; esr = er; break;
+        case kProg: Dprog = Dr; eprog = er; break;
+        default: Dlane = Dr; elane = er; break;
+      }
     }
     const bool wrap0 = (lane == 0);   // rows kDThr/kDSt of lane 0 are the non-local wrap rows
-    double Dw0 = shfl(D[kDThr], 0), Dw1 = shfl(D[kDSt], 0);
-    double ew0 = shfl(e[kDThr], 0), ew1 = shfl(e[kDSt], 0);
+    double Dw0 = shfl(Dthr, 0), Dw1 = shfl(Dst, 0);
+    double ew0 = shfl(ethr, 0), ew1 = shfl(esr, 0);
     Dw[0] = Dw0;
     Dw[1] = Dw1;
     // cost gradient / lane-row data of state `lane` live in the previous lane
@@ -491,7 +505,7 @@ struct WarpSolver {
       double t = shfl(gcost[k], prev_lane());
       gcp[k] = (lane == 0) ? 0.0 : t;
     }
-    double elane_p = shfl(e[kLane], prev_lane()), Dlane_p = shfl(D[kLane], prev_lane());
+    double elane_p = shfl(elane, prev_lane()), Dlane_p = shfl(Dlane, prev_lane());
     if (lane == 0) { elane_p = 0.0; Dlane_p = 0.0; }
     for (int k = 0; k < 3; ++k) {
       double t = shfl(gC[k], prev_lane());
@@ -505,24 +519,28 @@ struct WarpSolver {
     double* st = ws.st(lane);
     double* hs = st + kOffHs;
     double* gs = st + kOffGs;
-    const double dthr = wrap0 ? 0.0 : D[kDThr];
-    const double dst = wrap0 ? 0.0 : D[kDSt];
-    hs[27] = D[kProg];
+    const double* base = st + kOffBase;
+    const double dthr = wrap0 ? 0.0 : Dthr;
+    const double dst = wrap0 ? 0.0 : Dst;
+    // (X, Y, s) block of state `lane`: derivative part + lane-row Sigma term D gC gC'
+    hs[0] = hcp6[0] + Dlane_p * gCp[0] * gCp[0];
+    hs[1] = hcp6[1] + Dlane_p * gCp[0] * gCp[1];
+    hs[2] = hcp6[2] + Dlane_p * gCp[0] * gCp[2];
+    hs[3] = hcp6[3] + Dlane_p * gCp[1] * gCp[1];
+    hs[4] = hcp6[4] + Dlane_p * gCp[1] * gCp[2];
+    hs[5] = hcp6[5] + Dlane_p * gCp[2] * gCp[2];
+    hs[6 + hm_idx(4, 4)] = base[0] + Rtt + dthr;
+    hs[6 + hm_idx(5, 5)] = base[1] + Rss + dst + bq;
+    hs[27] = Dprog;
     hs[28] = dthr;
     hs[29] = dst + bq;
     hs[30] = -dthr;
     hs[31] = -(dst + bq);
-    st[kOffRow + 0] = D[kThrUb] + D[kThrLb] + dthr + D[kDThr0];
-    st[kOffRow + 1] = D[kStUb] + D[kStLb] + dst + bq + D[kDSt0];
-    st[kOffRow + 2] = Dlane_p;
-    st[kOffRow + 3] = gCp[0];
-    st[kOffRow + 4] = gCp[1];
-    st[kOffRow + 5] = gCp[2];
-    double eth = e[kThrUb] + e[kThrLb] + (wrap0 ? 0.0 : e[kDThr]) + e[kDThr0];
-    double est = e[kStUb] + e[kStLb] + (wrap0 ? 0.0 : e[kDSt]) + e[kDSt0];
+    double ethk = eth + (wrap0 ? 0.0 : ethr);
+    double estk = est + (wrap0 ? 0.0 : esr);
     if (cfg.wrap) {
-      if (lane == 0) { eth += ew0; est += ew1; }
-      if (lane == N - 1) { eth -= ew0; est -= ew1; }
+      if (lane == 0) { ethk += ew0; estk += ew1; }
+      if (lane == N - 1) { ethk -= ew0; estk -= ew1; }
     }
     const double bg = sgn * bsig * sigc_prev;
     gs[0] = sgn * gcp[0] + elane_p * gCp[0];
@@ -532,53 +550,42 @@ struct WarpSolver {
     gs[4] = sgn * gcp[4];
     gs[5] = 0.0;
     gs[6] = sgn * gcp[2] + elane_p * gCp[2];
-    gs[7] = wrap0 ? 0.0 : -e[kDThr];
-    gs[8] = (wrap0 ? 0.0 : -e[kDSt]) - bg;
-    gs[9] = eth;
-    gs[10] = est + bg;
-    gs[11] = e[kProg];
-    for (int k = 0; k < 6; ++k) st[kOffB + k] = -cv[k];
+    gs[7] = wrap0 ? 0.0 : -ethr;
+    gs[8] = (wrap0 ? 0.0 : -esr) - bg;
+    gs[9] = ethk;
+    gs[10] = estk + bg;
+    gs[11] = eprog;
+    for (int k = 0; k < 6; ++k) st[kOffB + k] = cv ? -cv[k] : 0.0;
     if (lane == N - 1) {
       double* gN = ws.st(N) + kOffGs;
-      double* lN = ws.st(N) + kOffRow;
-      gN[0] = sgn * gcost[0] + e[kLane] * gC[0];
-      gN[1] = sgn * gcost[1] + e[kLane] * gC[1];
+      double* hN = ws.st(N) + kOffHs;
+      const double* bN = ws.st(N) + kOffK;
+      gN[0] = sgn * gcost[0] + elane * gC[0];
+      gN[1] = sgn * gcost[1] + elane * gC[1];
       gN[2] = 0.0;
       gN[3] = sgn * gcost[3];
       gN[4] = sgn * gcost[4];
       gN[5] = 0.0;
-      gN[6] = sgn * gcost[2] + e[kLane] * gC[2];
+      gN[6] = sgn * gcost[2] + elane * gC[2];
       for (int k = 7; k < 12; ++k) gN[k] = 0.0;
-      lN[2] = D[kLane];
-      lN[3] = gC[0];
-      lN[4] = gC[1];
-      lN[5] = gC[2];
+      hN[0] = bN[0] + Dlane * gC[0] * gC[0];
+      hN[1] = bN[1] + Dlane * gC[0] * gC[1];
+      hN[2] = bN[2] + Dlane * gC[0] * gC[2];
+      hN[3] = bN[3] + Dlane * gC[1] * gC[1];
+      hN[4] = bN[4] + Dlane * gC[1] * gC[2];
+      hN[5] = bN[5] + Dlane * gC[2] * gC[2];
     }
   }
 
   // value of the assembled stage Hessian at a packed slot (+ regularisation flag)
   MPCR_D double stage_entry(const double* st, int slot, double dw) const {
-    const int sl = slot & 0xff;
-    double v = 0.0;
-    if (sl != 0xff) {
-      v = st[kOffHs + sl];
-      if (sl == 6 + hm_idx(4, 4)) v += st[kOffRow + 0];
-      if (sl == 6 + hm_idx(5, 5)) v += st[kOffRow + 1];
-      if (sl < 6) {          // lane-row Sigma term on (X, Y, s)
-        const double Dl = st[kOffRow + 2];
-        if (Dl != 0.0) {
-          const int ia = (sl < 3) ? 0 : ((sl < 5) ? 1 : 2);
-          const int ib = (sl < 3) ? sl : ((sl < 5) ? sl - 2 : 2);
-          v += Dl * st[kOffRow + 3 + ia] * st[kOffRow + 3 + ib];
-        }
-      }
-    }
+    double v = st[kOffHs + (slot & 0xff)];
     if (slot & 0x100) v += dw;
     return v;
   }
   MPCR_D static int slot_of(int r, int c) {
     int sl = hs_slot(r, c);
-    int slot = (sl < 0) ? 0xff : sl;
+    int slot = (sl < 0) ? kZeroSlot : sl;
     if (r == c && (r <= 6 || r == 9 || r == 10)) slot |= 0x100;
     return slot;
   }
@@ -614,10 +621,11 @@ struct WarpSolver {
     }
     syncwarp();
     bool ok = true;
+    const double dwc = dwflag * dw;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
       double* st = ws.st(k);
-      // ---- round 1: T = P M (rows), t_j = p_j + P b_j ; G <- stage Hessian ----
+      // ---- round 1: T = P M (rows), t_j = p_j + P b_j -----------------------------
       if (lane < 9) {
         double pr[9], A[21], out[12];
         for (int c = 0; c < 9; ++c) pr[c] = P[lane * 9 + c];
@@ -630,13 +638,9 @@ struct WarpSolver {
         ws.tv[9 + lane] = ws.pv[9 + lane];
         ws.tv[18 + lane] = ws.pv[18 + lane];
       }
-      for (int j = 0; j < 5; ++j) {
-        int e = lane + 32 * j;
-        if (e < 144) G[e] = stage_entry(st, gslot[j], dw);
-      }
       syncwarp();
-      // ---- round 2: G[:, c] += M' T[:, c] ; g_j = grad_j + M' t_j -----------------
-      if (lane < 12 + nrhs && lane != 7 && lane != 8) {
+      // ---- round 2: G[:, c] = M' T[:, c] + stage Hessian column ; g_j = grad_j + M' t_j
+      if (lane < 12 + nrhs) {
         const bool isvec = lane >= 12;
         const int j = lane - 12;
         double tc[9], A[21], out[12];
@@ -644,7 +648,8 @@ struct WarpSolver {
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(tc, A, Ts, out);
         if (!isvec) {
-          for (int r = 0; r < 12; ++r) G[r * 12 + lane] += out[r];
+          for (int r = 0; r < 12; ++r) G[r * 12 + lane] = out[r] + st[kOffHs + colslot[r]];
+          G[lane * 12 + lane] += dwc;
         } else {
           for (int r = 0; r < 12; ++r) {
             double g = out[r];
@@ -698,37 +703,48 @@ struct WarpSolver {
       syncwarp();
     }
     if (!ok) return false;
-    // ---- forward sweep (replicated in every lane; lane k keeps stage k) -----------
-    double z[kRhs][9];
+    // ---- forward sweep: lane groups 0-10 / 11-21 / 22-31 each roll out ONE right-hand side;
+    //      the group leaders park (z_{k+1}, w_k) in stage k's (now dead) gain slot -----------
+    const int grp = (nrhs == 1) ? 0 : (lane < 11 ? 0 : (lane < 22 ? 1 : 2));
+    const bool leader = (nrhs == 1) ? (lane == 0) : (lane == 0 || lane == 11 || lane == 22);
+    const double bsel = (grp == 0) ? 1.0 : 0.0;
+    double z[9];
+    for (int a = 0; a < 9; ++a) z[a] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      double* st = ws.st(k);
+      double A[21];
+      for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
+      double w[3];
+      for (int i = 0; i < 3; ++i) {
+        double acc = st[kOffKf + grp * 3 + i];
+        for (int a = 0; a < 9; ++a) acc += st[kOffK + i * 9 + a] * z[a];
+        w[i] = acc;
+      }
+      double zn[9];
+      applyM(z, w, A, Ts, zn);
+      for (int a = 0; a < 6; ++a) zn[a] += bsel * st[kOffB + a];
+      for (int a = 0; a < 9; ++a) z[a] = zn[a];
+      syncwarp();                       // every lane has read K_k before it is overwritten
+      if (leader) {
+        double* dst = st + kOffK + grp * 9;
+        for (int a = 0; a < 7; ++a) dst[a] = zn[a];
+        dst[7] = w[0];
+        dst[8] = w[1];
+      }
+    }
+    syncwarp();
     for (int j = 0; j < kRhs; ++j) {
-      for (int a = 0; a < 9; ++a) z[j][a] = 0.0;
       for (int a = 0; a < 7; ++a) mz[j][a] = 0.0;
       mw[j][0] = mw[j][1] = 0.0;
     }
-#pragma unroll 1
-    for (int k = 0; k < N; ++k) {
-      const double* st = ws.st(k);
-      double A[21];
-      for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
-#pragma unroll
+    if (act) {
+      const double* src = ws.st(lane) + kOffK;
       for (int j = 0; j < kRhs; ++j) {
         if (j < nrhs) {
-          double w[3];
-          for (int i = 0; i < 3; ++i) {
-            double acc = st[kOffKf + j * 3 + i];
-            for (int a = 0; a < 9; ++a) acc += st[kOffK + i * 9 + a] * z[j][a];
-            w[i] = acc;
-          }
-          double zn[9];
-          applyM(z[j], w, A, Ts, zn);
-          if (j == 0)
-            for (int a = 0; a < 6; ++a) zn[a] += st[kOffB + a];
-          for (int a = 0; a < 9; ++a) z[j][a] = zn[a];
-          if (k == lane) {
-            for (int a = 0; a < 7; ++a) mz[j][a] = zn[a];
-            mw[j][0] = w[0];
-            mw[j][1] = w[1];
-          }
+          for (int a = 0; a < 7; ++a) mz[j][a] = src[j * 9 + a];
+          mw[j][0] = src[j * 9 + 7];
+          mw[j][1] = src[j * 9 + 8];
         }
       }
     }
@@ -784,7 +800,7 @@ struct WarpSolver {
         for (int c = 0; c < 11; ++c) {
           if (c == 7 || c == 8) continue;
           const int slot = slot_of(a, c);
-          if (slot == 0xff) continue;
+          if (slot == kZeroSlot) continue;
           acc += stage_entry(st, slot, dw) * v12[c];
         }
         loc[lane * 7 + a] = acc;
@@ -796,7 +812,7 @@ struct WarpSolver {
           double acc = sN[kOffGs + a];
           for (int c = 0; c < 7; ++c) {
             const int slot = slot_of(a, c);
-            if (slot == 0xff) continue;
+            if (slot == kZeroSlot) continue;
             acc += stage_entry(sN, slot, dw) * vN[c];
           }
           loc[N * 7 + a] = acc;
@@ -968,7 +984,7 @@ struct WarpSolver {
     for (int r = 0; r < kNumRows; ++r) {
       double d = 0.0;
       if (on(r)) {
-        d = row_lin(r, du, dup, dsh, dshp, dx) + rdv[r];
+        d = row_lin(r, du, dup, dsh, dshp, dx) + (rdv ? rdv[r] : 0.0);
         if (row_hasL(r) && d < 0.0) a = fmin(a, -tau * (s[r] - lo(r)) / d);
         if (row_hasU(r) && d > 0.0) a = fmin(a, tau * (hi(r) - s[r]) / d);
       }
@@ -1054,9 +1070,8 @@ struct WarpSolver {
     double c_soc[6], d_soc[kNumRows];
     // plain (non-SOC) step saved while a second-order correction is being tried
     double sv_dx[6], sv_dsh = 0.0, sv_du[2] = {0.0, 0.0}, sv_dsr[kNumRows], sv_lam[6], sv_y0[7];
-    double zero_rows[kNumRows], zero6[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 1
-    for (int r = 0; r < kNumRows; ++r) { zero_rows[r] = 0.0; d_soc[r] = 0.0; sv_dsr[r] = 0.0; }
+    for (int r = 0; r < kNumRows; ++r) { d_soc[r] = 0.0; sv_dsr[r] = 0.0; }
     for (int a = 0; a < 6; ++a) { c_soc[a] = 0.0; sv_dx[a] = 0.0; sv_lam[a] = 0.0; }
     for (int a = 0; a < 7; ++a) sv_y0[a] = 0.0;
     Point tp;
@@ -1163,8 +1178,8 @@ struct WarpSolver {
       // ================= B. linear solve (single call site) ===================================
       if (phase == kPhInit || phase == kPhNewton || phase == kPhSoc) {
         const int mode = (phase == kPhInit) ? 1 : 0;
-        const double* rdv = (phase == kPhInit) ? zero_rows : ((phase == kPhSoc) ? d_soc : rd);
-        const double* cv = (phase == kPhInit) ? zero6 : ((phase == kPhSoc) ? c_soc : cres);
+        const double* rdv = (phase == kPhInit) ? nullptr : ((phase == kPhSoc) ? d_soc : rd);
+        const double* cv = (phase == kPhInit) ? nullptr : ((phase == kPhSoc) ? c_soc : cres);
         double dwu = (phase == kPhInit) ? 1.0 : dw;
         bool first_try = true, ok = false, failed = false;
 #pragma unroll 1
@@ -1269,9 +1284,7 @@ struct WarpSolver {
         tp.sh = sh + at * dsh;
         tp.u[0] = u[0] + at * du[0];
         tp.u[1] = u[1] + at * du[1];
-#pragma unroll 1
-        for (int r = 0; r < kNumRows; ++r) tp.s[r] = s[r] + at * dsr[r];
-        eval_point(tp);
+        eval_point(tp, at);
       }
       // ================= D. decisions ===========================================================
       if (phase == kPhInit) {
@@ -1381,28 +1394,23 @@ struct WarpSolver {
       const double astep = (phase == kPhSoc) ? a_soc : alpha;
       // dual steps: dyd = D ds + gsb - yd ; dv from the linearised complementarity
       double az = 1.0;
-      double dvL[kNumRows], dvU[kNumRows];
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
-        double a = 0.0, b = 0.0;
-        if (on(r)) {
-          double sg, gb;
-          sigma_gsb(r, sg, gb);
-          const double dyd = (sg + dw) * dsr[r] + gb - yd[r];
-          yd[r] += astep * dyd;
-          if (row_hasL(r)) {
-            const double sl = s[r] - lo(r);
-            a = mu / sl - vL[r] - vL[r] / sl * dsr[r];
-            if (a < 0.0) az = fmin(az, -tau * vL[r] / a);
-          }
-          if (row_hasU(r)) {
-            const double su = hi(r) - s[r];
-            b = mu / su - vU[r] + vU[r] / su * dsr[r];
-            if (b < 0.0) az = fmin(az, -tau * vU[r] / b);
-          }
+        if (!on(r)) continue;
+        double sg, gb;
+        sigma_gsb(r, sg, gb);
+        const double dyd = (sg + dw) * dsr[r] + gb - yd[r];
+        yd[r] += astep * dyd;
+        if (row_hasL(r)) {
+          const double sl = s[r] - lo(r);
+          const double a = mu / sl - vL[r] - vL[r] / sl * dsr[r];
+          if (a < 0.0) az = fmin(az, -tau * vL[r] / a);
         }
-        dvL[r] = a;
-        dvU[r] = b;
+        if (row_hasU(r)) {
+          const double su = hi(r) - s[r];
+          const double b = mu / su - vU[r] + vU[r] / su * dsr[r];
+          if (b < 0.0) az = fmin(az, -tau * vU[r] / b);
+        }
       }
       az = warp_min(az);
       for (int a = 0; a < 6; ++a) {
@@ -1420,18 +1428,22 @@ struct WarpSolver {
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
         if (!on(r)) continue;
-        s[r] = tp.s[r];
-        rd[r] = tp.rd[r];
+        const double sold = s[r];
+        const double snew = sold + astep * dsr[r];
         if (row_hasL(r)) {
-          const double sl = s[r] - lo(r);
-          double v = vL[r] + az * dvL[r];
+          const double slo = sold - lo(r), sl = snew - lo(r);
+          const double dv = mu / slo - vL[r] - vL[r] / slo * dsr[r];
+          const double v = vL[r] + az * dv;
           vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - s[r];
-          double v = vU[r] + az * dvU[r];
+          const double suo = hi(r) - sold, su = hi(r) - snew;
+          const double dv = mu / suo - vU[r] + vU[r] / suo * dsr[r];
+          const double v = vU[r] + az * dv;
           vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
         }
+        s[r] = snew;
+        rd[r] = tp.rd[r];
       }
       last_alpha = astep;
       it++;
