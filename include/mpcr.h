@@ -127,6 +127,33 @@ int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
 /* Launch geometry of the solve kernel: blocks, warps per block, dynamic shared bytes. */
 int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem_bytes);
 
+/* ---- track geometry (replaces splines/ParameterizedLine.py:19-105 and
+ * splines/ParameterizedCenterline.py:61-91 for batches of queries) -----------------------
+ * A track is a piecewise-cubic table: n pieces with break points brk[n+1] (brk[0] = 0,
+ * brk[n] = length) and local power-basis coefficients cx/cy[n,4] (lowest order first) of the
+ * reference's not-a-knot interpolating spline, plus the 0.5 m max-error table
+ * (lanes/<track>_max_error.csv: columns right, left; may be NULL / n_err = 0).
+ * Table pointers are HOST pointers (copied once); query arrays follow
+ * mpcr_config.pointers_on_device. */
+typedef struct mpcr_track mpcr_track;
+int mpcr_track_create(mpcr_handle* h, int n, const double* brk, const double* cx, const double* cy,
+                      int n_err, const double* err_right, const double* err_left,
+                      mpcr_track** out);
+int mpcr_track_destroy(mpcr_track* t);
+/* Gx, Gy, dGx, dGy, ddGx, ddGy at s[B] (any real, wrapped like `s % length`) -> out[B,6] */
+int mpcr_track_eval(mpcr_track* t, int B, const double* s, double* out, void* cuda_stream);
+/* x_as_coeffs / y_as_coeffs(s, lookahead, deg=4) -> cx[B,5], cy[B,5] (highest order first) */
+int mpcr_track_coeffs(mpcr_track* t, int B, const double* s, double lookahead, double* cx,
+                      double* cy, void* cuda_stream);
+/* projection(X, Y, bounds=(lo, hi)); NaN bounds or a window wider than 5 m = global search.
+ * Outputs s*[B], dist[B] and error_sign[B] (+1 right of the line, as error_sign(X, Y, s*)). */
+int mpcr_track_project(mpcr_track* t, int B, const double* X, const double* Y, const double* lo,
+                       const double* hi, double* s_out, double* dist_out, int32_t* sign_out,
+                       void* cuda_stream);
+/* lookup_error(s, lookahead) -> out[B] */
+int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, double lookahead, double* out,
+                            void* cuda_stream);
+
 /* Measured fp64 FMA peak of the device (DFMA-chain microbenchmark, TFLOP/s):
  * the roofline denominator for the solve kernel. */
 int mpcr_fp64_peak_tflops(mpcr_handle* h, double* tflops);

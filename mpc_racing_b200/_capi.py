@@ -42,6 +42,8 @@ EXPORTED_SYMBOLS = [
     "mpcr_version", "mpcr_config_default", "mpcr_create", "mpcr_destroy", "mpcr_last_error",
     "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
     "mpcr_launch_info", "mpcr_fp64_peak_tflops",
+    "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
+    "mpcr_track_project", "mpcr_track_lookup_error",
 ]
 
 _lib = None
@@ -83,6 +85,19 @@ def load_library(path=None):
     lib.mpcr_launch_info.restype = C.c_int
     lib.mpcr_fp64_peak_tflops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.mpcr_fp64_peak_tflops.restype = C.c_int
+    V = C.c_void_p
+    lib.mpcr_track_create.argtypes = [V, C.c_int, V, V, V, C.c_int, V, V, C.POINTER(V)]
+    lib.mpcr_track_create.restype = C.c_int
+    lib.mpcr_track_destroy.argtypes = [V]
+    lib.mpcr_track_destroy.restype = C.c_int
+    lib.mpcr_track_eval.argtypes = [V, C.c_int, V, V, V]
+    lib.mpcr_track_eval.restype = C.c_int
+    lib.mpcr_track_coeffs.argtypes = [V, C.c_int, V, C.c_double, V, V, V]
+    lib.mpcr_track_coeffs.restype = C.c_int
+    lib.mpcr_track_project.argtypes = [V, C.c_int, V, V, V, V, V, V, V, V]
+    lib.mpcr_track_project.restype = C.c_int
+    lib.mpcr_track_lookup_error.argtypes = [V, C.c_int, V, C.c_double, V, V]
+    lib.mpcr_track_lookup_error.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

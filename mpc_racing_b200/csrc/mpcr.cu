@@ -10,11 +10,15 @@
 
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <new>
 #include <string>
+#include <vector>
 
 #include "mpcr_config.h"
 #include "mpcr_ipm.cuh"
+#include "mpcr_track.cuh"
 
 namespace mpcr {
 
@@ -340,4 +344,274 @@ extern "C" int mpcr_fp64_peak_tflops(mpcr_handle* h, double* tflops) {
   const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
   *tflops = flops / (best * 1e-3) / 1e12;
   return MPCR_OK;
+}
+
+// =====================================================================================
+// Track kernels: one thread per query; the coefficient table is staged into shared memory
+// with ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier) when it fits, else the
+// kernel reads the table from global memory (lane-boundary splines have up to 8k pieces).
+// =====================================================================================
+namespace mpcr {
+
+struct TrackDev {
+  int n, n_err;
+  double length;
+  const double* table;    // packed: brk[n+1] | cx[4n] | cy[4n] | err_right[n_err] | err_left[n_err]
+  size_t bytes;           // padded to a multiple of 16
+};
+
+__device__ __forceinline__ TrackView make_view(const TrackDev& d, const double* base) {
+  TrackView v;
+  v.n = d.n;
+  v.length = d.length;
+  v.brk = base;
+  v.cx = base + (d.n + 1);
+  v.cy = v.cx + 4 * d.n;
+  v.n_err = d.n_err;
+  v.err_right = v.cy + 4 * d.n;
+  v.err_left = v.err_right + d.n_err;
+  return v;
+}
+
+// Stage `bytes` (multiple of 16, 16-byte aligned) from global to shared with a TMA bulk copy.
+__device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, unsigned bytes,
+                                          unsigned long long* bar) {
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(bar);
+  const unsigned dst_addr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(dst_addr), "l"(gsrc), "r"(bytes), "r"(bar_addr)
+        : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar_addr)
+        : "memory");
+  }
+}
+
+enum TrackOp : int { kOpEval = 0, kOpCoeffs = 1, kOpProject = 2, kOpLookup = 3 };
+
+struct TrackArgs {
+  int B;
+  const double* a0;   // s | s | X | s
+  const double* a1;   // - | - | Y | -
+  const double* a2;   // - | - | lo | -
+  const double* a3;   // - | - | hi | -
+  double scalar;      // - | lookahead | - | lookahead
+  double* o0;         // out[B,6] | cx[B,5] | s_out | out
+  double* o1;         // -        | cy[B,5] | dist  | -
+  int32_t* o2;        // -        | -       | sign  | -
+};
+
+template <int OP, bool STAGED>
+__global__ void __launch_bounds__(128) track_kernel(const TrackDev dev, const TrackArgs a) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  __shared__ __align__(8) unsigned long long bar;
+  const double* base = dev.table;
+  if (STAGED) {
+    tma_stage(tsm, dev.table, (unsigned)dev.bytes, &bar);
+    base = reinterpret_cast<const double*>(tsm);
+  }
+  const TrackView t = make_view(dev, base);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    if (OP == kOpEval) {
+      double o[6];
+      track_eval(t, a.a0[b], 2, o);
+      for (int k = 0; k < 6; ++k) a.o0[(size_t)b * 6 + k] = o[k];
+    } else if (OP == kOpCoeffs) {
+      double cx[5], cy[5];
+      track_fit4(t, a.a0[b], a.scalar, cx, cy);
+      for (int k = 0; k < 5; ++k) { a.o0[(size_t)b * 5 + k] = cx[k]; a.o1[(size_t)b * 5 + k] = cy[k]; }
+    } else if (OP == kOpProject) {
+      double s, d;
+      track_project(t, a.a0[b], a.a1[b], a.a2[b], a.a3[b], &s, &d);
+      a.o0[b] = s;
+      a.o1[b] = d;
+      if (a.o2) a.o2[b] = track_error_sign(t, a.a0[b], a.a1[b], s);
+    } else {
+      a.o0[b] = track_lookup_error(t, a.a0[b], a.scalar);
+    }
+  }
+}
+
+}  // namespace mpcr
+
+struct mpcr_track {
+  mpcr_handle* h;
+  TrackDev dev;
+  double* d_table = nullptr;
+  bool staged = false;
+  // staging for host-pointer queries
+  double* d_q = nullptr;
+  size_t q_doubles = 0;
+};
+
+static const size_t kTrackSmemLimit = 200 * 1024;
+
+extern "C" int mpcr_track_create(mpcr_handle* h, int n, const double* brk, const double* cx,
+                                 const double* cy, int n_err, const double* err_right,
+                                 const double* err_left, mpcr_track** out) {
+  if (!h || !out || n < 1 || !brk || !cx || !cy || n_err < 0 || (n_err > 0 && (!err_right || !err_left))) {
+    if (h) h->err = "mpcr_track_create: invalid argument";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  CK(cudaSetDevice(h->device));
+  mpcr_track* t = new (std::nothrow) mpcr_track();
+  if (!t) return MPCR_ERR_INVALID_ARG;
+  t->h = h;
+  size_t nd = (size_t)(n + 1) + 8 * (size_t)n + 2 * (size_t)n_err;
+  nd = (nd + 1) & ~(size_t)1;                 // 16-byte multiple
+  std::vector<double> host(nd, 0.0);
+  double* p = host.data();
+  memcpy(p, brk, (n + 1) * sizeof(double)); p += n + 1;
+  memcpy(p, cx, 4 * (size_t)n * sizeof(double)); p += 4 * (size_t)n;
+  memcpy(p, cy, 4 * (size_t)n * sizeof(double)); p += 4 * (size_t)n;
+  if (n_err) {
+    memcpy(p, err_right, n_err * sizeof(double)); p += n_err;
+    memcpy(p, err_left, n_err * sizeof(double));
+  }
+  cudaError_t e = cudaMalloc(&t->d_table, nd * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_table, host.data(), nd * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    h->err = std::string("mpcr_track_create: ") + cudaGetErrorString(e);
+    if (t->d_table) cudaFree(t->d_table);
+    delete t;
+    return MPCR_ERR_CUDA;
+  }
+  t->dev.n = n;
+  t->dev.n_err = n_err;
+  t->dev.length = brk[n];
+  t->dev.table = t->d_table;
+  t->dev.bytes = nd * sizeof(double);
+  t->staged = t->dev.bytes <= kTrackSmemLimit;
+  *out = t;
+  return MPCR_OK;
+}
+
+extern "C" int mpcr_track_destroy(mpcr_track* t) {
+  if (!t) return MPCR_ERR_INVALID_ARG;
+  cudaSetDevice(t->h->device);
+  if (t->d_table) cudaFree(t->d_table);
+  if (t->d_q) cudaFree(t->d_q);
+  delete t;
+  return MPCR_OK;
+}
+
+template <int OP>
+static int track_launch(mpcr_track* t, const TrackArgs& a, cudaStream_t st) {
+  mpcr_handle* h = t->h;
+  const int threads = 128;
+  int blocks = (a.B + threads - 1) / threads;
+  const int cap = h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (t->staged) {
+    CK(cudaFuncSetAttribute(track_kernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)t->dev.bytes));
+    track_kernel<OP, true><<<blocks, threads, t->dev.bytes, st>>>(t->dev, a);
+  } else {
+    track_kernel<OP, false><<<blocks, threads, 0, st>>>(t->dev, a);
+  }
+  CK(cudaGetLastError());
+  return MPCR_OK;
+}
+
+// generic driver: nin input arrays of B doubles, outputs of given widths
+static int track_run(mpcr_track* t, int op, int B, const double* const* in, int nin, double scalar,
+                     double* const* outp, const int* out_w, int nout, int32_t* sign_out, void* stream) {
+  if (!t) return MPCR_ERR_INVALID_ARG;
+  mpcr_handle* h = t->h;
+  if (B < 0) { h->err = "negative batch"; return MPCR_ERR_INVALID_ARG; }
+  if (B == 0) return MPCR_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* din[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* dout[2] = {nullptr, nullptr};
+  int32_t* dsign = nullptr;
+  const bool on_dev = h->pub.pointers_on_device != 0;
+  if (on_dev) {
+    for (int i = 0; i < nin; ++i) din[i] = in[i];
+    for (int i = 0; i < nout; ++i) dout[i] = outp[i];
+    dsign = sign_out;
+  } else {
+    size_t need = (size_t)B * nin;
+    for (int i = 0; i < nout; ++i) need += (size_t)B * out_w[i];
+    need += (size_t)B;     // sign (int32 in a double slot)
+    if (need > t->q_doubles) {
+      if (t->d_q) cudaFree(t->d_q);
+      t->d_q = nullptr;
+      t->q_doubles = 0;
+      CK(cudaMalloc(&t->d_q, need * sizeof(double)));
+      t->q_doubles = need;
+    }
+    double* p = t->d_q;
+    for (int i = 0; i < nin; ++i) {
+      CK(cudaMemcpyAsync(p, in[i], (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+      din[i] = p;
+      p += B;
+    }
+    for (int i = 0; i < nout; ++i) { dout[i] = p; p += (size_t)B * out_w[i]; }
+    dsign = sign_out ? reinterpret_cast<int32_t*>(p) : nullptr;
+  }
+  TrackArgs a{B, din[0], din[1], din[2], din[3], scalar, dout[0], dout[1], dsign};
+  int rc;
+  if (op == kOpEval) rc = track_launch<kOpEval>(t, a, st);
+  else if (op == kOpCoeffs) rc = track_launch<kOpCoeffs>(t, a, st);
+  else if (op == kOpProject) rc = track_launch<kOpProject>(t, a, st);
+  else rc = track_launch<kOpLookup>(t, a, st);
+  if (rc != MPCR_OK) return rc;
+  if (!on_dev) {
+    for (int i = 0; i < nout; ++i)
+      CK(cudaMemcpyAsync(outp[i], dout[i], (size_t)B * out_w[i] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sign_out)
+      CK(cudaMemcpyAsync(sign_out, dsign, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return MPCR_OK;
+}
+
+extern "C" int mpcr_track_eval(mpcr_track* t, int B, const double* s, double* out, void* stream) {
+  const double* in[1] = {s};
+  double* o[1] = {out};
+  const int w[1] = {6};
+  return track_run(t, kOpEval, B, in, 1, 0.0, o, w, 1, nullptr, stream);
+}
+
+extern "C" int mpcr_track_coeffs(mpcr_track* t, int B, const double* s, double lookahead, double* cx,
+                                 double* cy, void* stream) {
+  const double* in[1] = {s};
+  double* o[2] = {cx, cy};
+  const int w[2] = {5, 5};
+  return track_run(t, kOpCoeffs, B, in, 1, lookahead, o, w, 2, nullptr, stream);
+}
+
+extern "C" int mpcr_track_project(mpcr_track* t, int B, const double* X, const double* Y,
+                                  const double* lo, const double* hi, double* s_out, double* dist_out,
+                                  int32_t* sign_out, void* stream) {
+  const double* in[4] = {X, Y, lo, hi};
+  double* o[2] = {s_out, dist_out};
+  const int w[2] = {1, 1};
+  return track_run(t, kOpProject, B, in, 4, 0.0, o, w, 2, sign_out, stream);
+}
+
+extern "C" int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, double lookahead,
+                                       double* out, void* stream) {
+  if (t && t->dev.n_err == 0) { t->h->err = "track has no max-error table"; return MPCR_ERR_INVALID_ARG; }
+  const double* in[1] = {s};
+  double* o[1] = {out};
+  const int w[1] = {1};
+  return track_run(t, kOpLookup, B, in, 1, lookahead, o, w, 1, nullptr, stream);
 }

@@ -62,3 +62,43 @@ extern "C" void emu_model_lin(int model, const double* x, const double* u, doubl
   for (int i = 0; i < 3; ++i)
     for (int k = 0; k < 2; ++k) lin21[15 + 2 * i + k] = L.bu[i][k];
 }
+
+// ---- track geometry: the same host/device functions the CUDA track kernels call ------------
+#include "../../mpc_racing_b200/csrc/mpcr_track.cuh"
+
+static mpcr::TrackView emu_view(int n, const double* brk, const double* cx, const double* cy,
+                                int n_err, const double* er, const double* el) {
+  mpcr::TrackView t;
+  t.n = n; t.length = brk[n]; t.brk = brk; t.cx = cx; t.cy = cy;
+  t.n_err = n_err; t.err_right = er; t.err_left = el;
+  return t;
+}
+
+extern "C" void emu_track_eval(int n, const double* brk, const double* cx, const double* cy, int B,
+                               const double* s, double* out) {
+  mpcr::TrackView t = emu_view(n, brk, cx, cy, 0, nullptr, nullptr);
+  for (int b = 0; b < B; ++b) mpcr::track_eval(t, s[b], 2, out + 6 * b);
+}
+
+extern "C" void emu_track_coeffs(int n, const double* brk, const double* cx, const double* cy, int B,
+                                 const double* s, double lookahead, double* ocx, double* ocy) {
+  mpcr::TrackView t = emu_view(n, brk, cx, cy, 0, nullptr, nullptr);
+  for (int b = 0; b < B; ++b) mpcr::track_fit4(t, s[b], lookahead, ocx + 5 * b, ocy + 5 * b);
+}
+
+extern "C" void emu_track_project(int n, const double* brk, const double* cx, const double* cy, int B,
+                                  const double* X, const double* Y, const double* lo, const double* hi,
+                                  double* s_out, double* d_out, int32_t* sign_out) {
+  mpcr::TrackView t = emu_view(n, brk, cx, cy, 0, nullptr, nullptr);
+  for (int b = 0; b < B; ++b) {
+    mpcr::track_project(t, X[b], Y[b], lo[b], hi[b], s_out + b, d_out + b);
+    sign_out[b] = mpcr::track_error_sign(t, X[b], Y[b], s_out[b]);
+  }
+}
+
+extern "C" void emu_track_lookup_error(int n, const double* brk, const double* cx, const double* cy,
+                                       int n_err, const double* er, const double* el, int B,
+                                       const double* s, double lookahead, double* out) {
+  mpcr::TrackView t = emu_view(n, brk, cx, cy, n_err, er, el);
+  for (int b = 0; b < B; ++b) out[b] = mpcr::track_lookup_error(t, s[b], lookahead);
+}
