@@ -154,6 +154,12 @@ int mpcr_track_project(mpcr_track* t, int B, const double* X, const double* Y, c
 int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, double lookahead, double* out,
                             void* cuda_stream);
 
+/* ---- plant step (closed-loop rollouts): x_out[b] = <Model>BicycleModel(x[b]).step(u[b,0],
+ * u[b,1], dt) of models/KinematicBicycleModel.py:11-48, DynamicBicycleModel.py:16-78,
+ * BlendedBicycleModel.py:18-58 (model = MPCR_MODEL_*).  x, x_out [B,6]; u [B,2]. */
+int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x, const double* u, double dt,
+                    double* x_out, void* cuda_stream);
+
 /* Measured fp64 FMA peak of the device (DFMA-chain microbenchmark, TFLOP/s):
  * the roofline denominator for the solve kernel. */
 int mpcr_fp64_peak_tflops(mpcr_handle* h, double* tflops);

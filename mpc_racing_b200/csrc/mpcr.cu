@@ -615,3 +615,55 @@ extern "C" int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, do
   const int w[1] = {1};
   return track_run(t, kOpLookup, B, in, 1, lookahead, o, w, 1, nullptr, stream);
 }
+
+// =====================================================================================
+// Plant step (closed-loop rollouts): x_out[b] = model.step(u[b], dt) of models/*.py
+// =====================================================================================
+#include "mpcr_plant.cuh"
+
+namespace mpcr {
+__global__ void __launch_bounds__(128) plant_kernel(int model, int B, const double* __restrict__ x,
+                                                    const double* __restrict__ u, double dt,
+                                                    double* __restrict__ out) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    double xi[6], ui[2], o[6];
+    for (int k = 0; k < 6; ++k) xi[k] = x[(size_t)b * 6 + k];
+    ui[0] = u[(size_t)b * 2];
+    ui[1] = u[(size_t)b * 2 + 1];
+    plant_step(model, xi, ui, dt, o);
+    for (int k = 0; k < 6; ++k) out[(size_t)b * 6 + k] = o[k];
+  }
+}
+}  // namespace mpcr
+
+extern "C" int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x, const double* u,
+                               double dt, double* x_out, void* stream) {
+  if (!h || !x || !u || !x_out || B < 0 || model < 0 || model > 2) {
+    if (h) h->err = "mpcr_plant_step: invalid argument";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  if (B == 0) return MPCR_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 128;
+  int blocks = (B + threads - 1) / threads;
+  if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+  if (h->pub.pointers_on_device) {
+    plant_kernel<<<blocks, threads, 0, st>>>(model, B, x, u, dt, x_out);
+    CK(cudaGetLastError());
+    return MPCR_OK;
+  }
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)B * 14 * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d, x, (size_t)B * 6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + (size_t)B * 6, u, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    plant_kernel<<<blocks, threads, 0, st>>>(model, B, d, d + (size_t)B * 6, dt, d + (size_t)B * 8);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(x_out, d + (size_t)B * 8, (size_t)B * 6 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { h->err = std::string("mpcr_plant_step: ") + cudaGetErrorString(e); return MPCR_ERR_CUDA; }
+  return MPCR_OK;
+}

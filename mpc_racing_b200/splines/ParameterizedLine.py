@@ -65,6 +65,25 @@ class ParameterizedLine:
             raise _capi.MpcrError(owner.lib.mpcr_last_error(owner._h).decode())
         self._track = out
 
+    def device_track(self, owner):
+        """A second mpcr_track bound to ``owner`` (a BatchedMPC created with on_device=True):
+        query arrays are then device pointers.  Returns the raw handle; the caller destroys it
+        with ``owner.lib.mpcr_track_destroy``."""
+        t = self._tables
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        er = el = None
+        n_err = 0
+        if self._err is not None:
+            er = np.ascontiguousarray(self._err[:, 1], dtype=np.float64)
+            el = np.ascontiguousarray(self._err[:, 2], dtype=np.float64)
+            n_err = len(er)
+        out = C.c_void_p()
+        rc = owner.lib.mpcr_track_create(owner._h, len(t["brk"]) - 1, p(t["brk"]), p(t["cx"]), p(t["cy"]),
+                                         n_err, p(er), p(el), C.byref(out))
+        if rc != 0:
+            raise _capi.MpcrError(owner.lib.mpcr_last_error(owner._h).decode())
+        return out
+
     def _free(self):
         if getattr(self, "_track", None):
             self._owner.lib.mpcr_track_destroy(self._track)

@@ -102,3 +102,10 @@ extern "C" void emu_track_lookup_error(int n, const double* brk, const double* c
   mpcr::TrackView t = emu_view(n, brk, cx, cy, n_err, er, el);
   for (int b = 0; b < B; ++b) out[b] = mpcr::track_lookup_error(t, s[b], lookahead);
 }
+
+// ---- plant models ------------------------------------------------------------------------------
+#include "../../mpc_racing_b200/csrc/mpcr_plant.cuh"
+extern "C" void emu_plant_step(int model, int B, const double* x, const double* u, const double* dt,
+                               double* out) {
+  for (int b = 0; b < B; ++b) mpcr::plant_step(model, x + 6 * b, u + 2 * b, dt[b], out + 6 * b);
+}

@@ -1,0 +1,112 @@
+"""Closed-loop rollouts and the GA fitness loop (config 5) on the GPU.
+
+The reference never closes the loop outside CARLA; parity here means: same plant step + same
+per-step preparation + same MPC solve, compared step by step against a CPU loop built from the
+oracle pieces (oracle/splines.py, oracle/ipm.py, oracle/plant.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def t4():
+    from mpc_racing_b200.splines import ParameterizedCenterline
+    return ParameterizedCenterline("t4")
+
+
+def test_plant_kernel_matches_reference_models():
+    from mpc_racing_b200.solver import BatchedMPC
+    import ctypes as C
+    g = np.load(os.path.join(GOLD, "plant_golden.npz"))
+    s = BatchedMPC()
+    for name, mid in (("dynamic", 0), ("kinematic", 1), ("blended", 2)):
+        for dt in (0.05, 0.1):
+            sel = g["dt"] == dt
+            x = np.ascontiguousarray(g["x0"][sel])
+            u = np.ascontiguousarray(g["u"][sel])
+            out = np.empty_like(x)
+            rc = s.lib.mpcr_plant_step(s._h, mid, len(x), x.ctypes.data, u.ctypes.data, dt, out.ctypes.data, None)
+            assert rc == 0
+            np.testing.assert_allclose(out, g[name][sel], rtol=1e-12, atol=1e-11)
+
+
+def test_closed_loop_steps_match_cpu_loop(t4):
+    from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
+    from oracle import plant, splines as osp
+    from parity_util import oracle_solve
+    ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="blended")
+    R, K = 3, 4
+    x0, s0 = start_states(t4, R, seed=7, v0=8.0)
+    res = ro.run(x0, s0, max_steps=K, record=True)
+    hist = res["history"]
+    ocl = osp.Centerline("t4", lanes=False)
+    for r in range(R):
+        x = x0[r].copy()
+        prog = s0[r]
+        u_prev = np.zeros(2)
+        u_warm = None
+        for k in range(K):
+            lo, hi = (prog - 2) % ocl.length, (prog + 2) % ocl.length
+            b = (lo, hi) if lo < hi else (hi, lo)
+            if 5 < abs(b[1] - b[0]):
+                pytest.skip("start state at the wrap: the reference would call dual_annealing")
+            prog, _ = ocl.projection_local(x[0], x[1], bounds=b)
+            np.testing.assert_allclose(hist[k]["progress"][r], prog, rtol=0, atol=1e-6)
+            cx = ocl.x_as_coeffs(prog - 5, 45, 4)
+            cy = ocl.y_as_coeffs(prog - 5, 45, 4)
+            ref = oracle_solve(x, u_prev, prog, cx, cy, N=15, Ts=0.05, u_warm=u_warm)
+            assert int(hist[k]["status"][r]) == ref["status"]
+            np.testing.assert_allclose(hist[k]["u0"][r], ref["U"][:, 0], rtol=0, atol=2e-4)
+            np.testing.assert_allclose(hist[k]["x"][r], x, rtol=0, atol=1e-4)
+            u0 = ref["U"][:, 0]
+            x = plant.blended_step(x, u0, 0.05)
+            u_prev = u0
+            u_warm = ref["U"]
+    ro.close()
+
+
+def test_lap_rollouts_and_segments(t4):
+    """A batch of full laps on t4: every vehicle finishes, stays on the track, segment times add
+    up to the lap time."""
+    from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
+    from mpc_racing_b200.splines.TrackSegments import TrackSegments
+    seg = TrackSegments(t4, 5, 30, 1500, 1500, 250)
+    gold = np.load(os.path.join(GOLD, "splines_golden.npz"))["t4/segments"]
+    assert abs(seg.lap_time - gold[0]) <= 2e-4 * gold[0]
+    np.testing.assert_allclose(seg.bounds, gold[1:], rtol=2e-4, atol=0.2)
+    ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="blended")
+    R = 64
+    x0, s0 = start_states(t4, R, seed=11, v0=5.0)
+    bounds = [b for b in seg.bounds]
+    bounds[-1] = t4.length
+    res = ro.run(x0, s0, max_steps=2500, seg_bounds=bounds)
+    fin = ~np.isnan(res["lap_time"])
+    assert fin.mean() >= 0.9, fin.mean()
+    assert np.nanmedian(res["lap_time"]) < 125.0
+    assert (res["max_abs_error"][fin] < 9.2).all()            # inside the lane half-width of t4
+    st = res["seg_times"][fin]
+    np.testing.assert_allclose(st.sum(axis=1), res["lap_time"][fin], rtol=0, atol=1e-9)
+    ro.close()
+
+
+def test_ga_generation(t4):
+    from mpc_racing_b200.GA import mpcGA
+    from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
+    from mpc_racing_b200.splines.TrackSegments import TrackSegments
+    seg = TrackSegments(t4, mpcGA.num_checkpoints, 30, 1500, 1500, 250)
+    ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="blended")
+    # a short course: the first checkpoint segment only, population 16
+    bounds = [0.0] + [seg.bounds[1] * f for f in (0.2, 0.4, 0.6, 0.8, 1.0)]
+    ga = mpcGA.GeneticAlgorithm(ro, bounds, seg.lap_time / mpcGA.num_checkpoints, pop=16, seed=3)
+    x0, s0 = start_states(t4, 1, seed=5, v0=10.0)
+    before = ga.population.copy()
+    out = ga.run_step(x0[0], s0, max_steps=260)
+    assert out["rewards"].shape == (16,) and np.isfinite(out["rewards"]).all() and out["best_reward"] > 0
+    assert (ga.population != before).any()
+    prm = mpcGA.decode(ga.population)
+    assert ((prm[:, 3] == 2) | (prm[:, 3] == 4)).all() and (prm[:, 1] >= 0.5).all()
+    ro.close()

@@ -119,3 +119,16 @@ def test_coeffs_projection_lookup(lines, sg, lib, track):
         lib.emu_track_lookup_error(n, _p(t["brk"]), _p(t["cx"]), _p(t["cy"]), len(er), _p(er), _p(el), len(sq),
                                    _p(sq), la, _p(out))
         np.testing.assert_array_equal(out, sg[f"{track}/lookup_error"][:, li])
+
+
+def test_plant_device_functions_match_reference(lib):
+    """csrc/mpcr_plant.cuh (host build) vs golden vectors of the reference's models/*.py."""
+    g = np.load(os.path.join(GOLD, "plant_golden.npz"))
+    lib.emu_plant_step.argtypes = [C.c_int, C.c_int, V, V, V, V]
+    x0 = np.ascontiguousarray(g["x0"])
+    u = np.ascontiguousarray(g["u"])
+    dt = np.ascontiguousarray(g["dt"])
+    for name, mid in (("dynamic", 0), ("kinematic", 1), ("blended", 2)):
+        out = np.empty_like(x0)
+        lib.emu_plant_step(mid, len(x0), _p(x0), _p(u), _p(dt), _p(out))
+        np.testing.assert_allclose(out, g[name], rtol=1e-13, atol=1e-12)
