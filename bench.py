@@ -151,8 +151,9 @@ def run_gpu(args):
 
     B = args.batch
     # independent problems: rank r owns batch indices [r*B, (r+1)*B) of the global batch
+    from mpc_racing_b200.sharding import shard_range
     full = make_batch(B * world)
-    sl = slice(rank * B, (rank + 1) * B)
+    sl = slice(*shard_range(B * world, rank, world))
     host = {k: np.ascontiguousarray(v[sl]) for k, v in full.items()}
     dsolver = BatchedMPC(N=N_HORIZON, Ts=TS, model="dynamic", device=local, on_device=True)
     hsolver = BatchedMPC(N=N_HORIZON, Ts=TS, model="dynamic", device=local, on_device=False)
