@@ -40,19 +40,27 @@ MPCR_D double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v,
 MPCR_D int shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 #endif
 
-MPCR_D double warp_sum(double v) {
+#if defined(__CUDACC__)
+#define MPCR_NOINLINE __device__ __noinline__
+#else
+#define MPCR_NOINLINE inline
+#endif
+
+MPCR_NOINLINE double powd(double x, double y) { return pow(x, y); }
+
+MPCR_NOINLINE double warp_sum(double v) {
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
   return v;
 }
-MPCR_D double warp_max(double v) {
+MPCR_NOINLINE double warp_max(double v) {
   for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m));
   return v;
 }
-MPCR_D double warp_min(double v) {
+MPCR_NOINLINE double warp_min(double v) {
   for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m));
   return v;
 }
-MPCR_D bool warp_all(bool p) {
+MPCR_NOINLINE bool warp_all(bool p) {
   int v = p ? 1 : 0;
   for (int m = 16; m > 0; m >>= 1) v &= shfl_xor_i(v, m);
   return v != 0;
@@ -356,7 +364,7 @@ struct WarpSolver {
       }
       t.rd[r] = rdv;
     }
-    double bar = act ? (-log(prod) + o.kappa_d * lin) : 0.0;
+    double bar = act ? (-log_d(prod) + o.kappa_d * lin) : 0.0;
     fin = fin && finite_d(fl) && finite_d(th) && finite_d(bar);
     t.finite = warp_all(fin);
     t.f = df * warp_sum(fl);
@@ -1163,7 +1171,7 @@ struct WarpSolver {
               // monotone barrier update (Waechter & Biegler eq. (7))
               if (e.E <= o.barrier_tol_factor * mu && mu > mu_floor) {
                 mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
-                                         pow(mu, o.mu_superlinear_decrease_power)));
+                                         powd(mu, o.mu_superlinear_decrease_power)));
                 tau = fmax(o.tau_min, 1.0 - mu);
                 filt_n = 0;
               } else {
@@ -1252,7 +1260,7 @@ struct WarpSolver {
           if (gpd < 0.0) {
             amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
             if (theta <= theta_min)
-              amin = fmin(amin, o.delta * pow(theta, o.s_theta) / pow(-gpd, o.s_phi));
+              amin = fmin(amin, o.delta * powd(theta, o.s_theta) / powd(-gpd, o.s_phi));
           } else {
             amin = o.gamma_theta;
           }
@@ -1327,7 +1335,7 @@ struct WarpSolver {
       bool ok = tp.finite && tp.theta <= theta_max;
       if (ok) {
         const bool switching = gpd < 0.0 &&
-            alpha * pow(-gpd, o.s_phi) > o.delta * pow(theta, o.s_theta);
+            alpha * powd(-gpd, o.s_phi) > o.delta * powd(theta, o.s_theta);
         if (theta <= theta_min && switching) {
           ok = cmp_le(tphi - phi, o.eta_phi * alpha * gpd, phi);
           f_type = true;

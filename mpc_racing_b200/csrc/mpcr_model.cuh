@@ -9,6 +9,27 @@
 
 namespace mpcr {
 
+// Double-precision libm expansions are 100-250 SASS instructions each; on the device they are
+// wrapped in non-inlined functions so that the solve kernel's hot loop stays inside the SM's
+// instruction cache (profiles/r1a: the first version was instruction-fetch bound).
+#if defined(__CUDACC__)
+#define MPCR_MATH __host__ __device__ __noinline__
+#else
+#define MPCR_MATH inline
+#endif
+MPCR_MATH void sincos_d(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(a, s, c);
+#else
+  *s = sin(a);
+  *c = cos(a);
+#endif
+}
+MPCR_MATH double atan2_d(double y, double x) { return atan2(y, x); }
+MPCR_MATH double exp_d(double x) { return exp(x); }
+MPCR_MATH double log_d(double x) { return log(x); }
+MPCR_MATH double rcp_d(double x) { return 1.0 / x; }
+
 // models/VehicleParameters.py:8-41 (pi ~ 3.14 exactly as the reference writes it)
 namespace vp {
 constexpr double m = 1845.0;
@@ -84,15 +105,17 @@ MPCR_HD void f_dynamic(const double* x, const double* u, double Ts, double* f) {
   double yaw = x[2], v_x = x[3], v_y = x[4], r = x[5];
   double fx = Fx_force(u[0], v_x);
   double delta = steer_angle(u[1], v_x, v_y);
-  double thf = atan2(v_y + vp::lf * r, v_x + 0.1);
-  double thr = atan2(v_y - vp::lr * r, v_x + 0.1);
+  double thf = atan2_d(v_y + vp::lf * r, v_x + 0.1);
+  double thr = atan2_d(v_y - vp::lr * r, v_x + 0.1);
   double Fyf = vp::Cf * (delta - thf);
   double Fyr = vp::Cr * (-thr);
-  double sd = sin(delta), cd = cos(delta);
+  double sd, cd;
+  sincos_d(delta, &sd, &cd);
   double vxd = ((fx - Fyf * sd) / vp::m) + (v_y * r);
   double vyd = ((Fyf * cd + Fyr) / vp::m) - (v_x * r);
   double rd = ((Fyf * cd * vp::lf) - (Fyr * vp::lr)) / vp::Iz;
-  double sy = sin(yaw), cy = cos(yaw);
+  double sy, cy;
+  sincos_d(yaw, &sy, &cy);
   f[0] = x[0] + (v_x * cy - v_y * sy) * Ts;
   f[1] = x[1] + (v_x * sy + v_y * cy) * Ts;
   f[2] = yaw + r * Ts;
@@ -106,7 +129,8 @@ MPCR_HD void f_kinematic(const double* x, const double* u, double Ts, double* f)
   double yaw = x[2], v_x = x[3], v_y = x[4], r = x[5];
   double fx = Fx_force(u[0], v_x);
   double delta = steer_angle(u[1], v_x, v_y);
-  double sy = sin(yaw), cy = cos(yaw);
+  double sy, cy;
+  sincos_d(yaw, &sy, &cy);
   f[0] = x[0] + (v_x * cy - v_y * sy) * Ts;
   f[1] = x[1] + (v_x * sy + v_y * cy) * Ts;
   f[2] = yaw + r * Ts;
@@ -179,7 +203,8 @@ MPCR_HD void common_eval(const double* x, const double* u, Common& c) {
 MPCR_HD void position_rows(const double* x, double Ts, const double* lam, StageLin& L,
                            double* hm /* may be null */) {
   double yaw = x[2], v_x = x[3], v_y = x[4];
-  double s = sin(yaw), c = cos(yaw);
+  double s, c;
+  sincos_d(yaw, &s, &c);
   L.aX[0] = (-v_x * s - v_y * c) * Ts;
   L.aX[1] = c * Ts;
   L.aX[2] = -s * Ts;
@@ -205,11 +230,12 @@ MPCR_HD void lin_dynamic(const double* x, const double* u, double Ts, const doub
   double af = v_y + vp::lf * r, ar = v_y - vp::lr * r;
   double Df = af * af + b * b, Dr = ar * ar + b * b;
   double iDf = 1.0 / Df, iDr = 1.0 / Dr;
-  double thf = atan2(af, b), thr = atan2(ar, b);
+  double thf = atan2_d(af, b), thr = atan2_d(ar, b);
   // gradients over q = (v_x, v_y, r, thr, st)
   double gthf[3] = {-af * iDf, b * iDf, vp::lf * b * iDf};
   double gthr[3] = {-ar * iDr, b * iDr, -vp::lr * b * iDr};
-  double sd = sin(c.delta), cd = cos(c.delta);
+  double sd, cd;
+  sincos_d(c.delta, &sd, &cd);
   double Fyf = vp::Cf * (c.delta - thf);
   double Fyr = -vp::Cr * thr;
   double gd[5] = {c.gd_vx, c.gd_vy, 0.0, 0.0, c.gd_st};
@@ -236,7 +262,8 @@ MPCR_HD void lin_dynamic(const double* x, const double* u, double Ts, const doub
     double vxd = ((c.fx - Fyf * sd) / vp::m) + (v_y * r);
     double vyd = ((Fyf * cd + Fyr) / vp::m) - (v_x * r);
     double rd = ((Fyf * cd * vp::lf) - (Fyr * vp::lr)) / vp::Iz;
-    double sy = sin(x[2]), cy = cos(x[2]);
+    double sy, cy;
+    sincos_d(x[2], &sy, &cy);
     f[0] = x[0] + (v_x * cy - v_y * sy) * Ts;
     f[1] = x[1] + (v_x * sy + v_y * cy) * Ts;
     f[2] = x[2] + r * Ts;
@@ -320,7 +347,8 @@ MPCR_HD void lin_kinematic(const double* x, const double* u, double Ts, const do
   double td = tan(c.delta);
   double sec2 = 1.0 + td * td;
   if (f) {
-    double sy = sin(x[2]), cy = cos(x[2]);
+    double sy, cy;
+    sincos_d(x[2], &sy, &cy);
     f[0] = x[0] + (v_x * cy - x[4] * sy) * Ts;
     f[1] = x[1] + (v_x * sy + x[4] * cy) * Ts;
     f[2] = x[2] + r * Ts;
@@ -481,7 +509,7 @@ MPCR_HD void stage_cost(const Params& p, const double* cx, const double* cy, con
   o.eC = eC;
   o.eL = eL;
   double v_x = x[3], v_y = x[4];
-  double ex = exp(p.q_v_max * (v_x - p.v_max));
+  double ex = exp_d(p.q_v_max * (v_x - p.v_max));
   double eCn1 = ipow(eC, p.n_exp - 1);
   o.val = p.q_v_y * v_y * v_y + p.alpha_c * eCn1 * eC + p.alpha_L * eL * eL + ex;
   if (order < 1) return;
