@@ -857,10 +857,20 @@ struct WarpSolver {
   // -------------------------------------------------------------------------
   // Optimality error E_mu (Waechter & Biegler eq. (5)) and its ingredients
   // -------------------------------------------------------------------------
-  struct Errors { double E, dual_inf, pr_inf, compl_inf; };
+  // One pass gives E_mu for EVERY mu: only the complementarity term depends on mu and
+  // max_i |p_i - mu| = max(|p_max - mu|, |p_min - mu|) over the products p_i = slack_i * v_i.
+  struct Errors {
+    double dual_inf, pr_inf, prod_max, prod_min, s_d, s_c, viol;
+    MPCR_D double compl_inf(double mu_t) const {
+      return fmax(fabs(prod_max - mu_t), fabs(prod_min - mu_t));
+    }
+    MPCR_D double E(double mu_t) const {
+      return fmax(dual_inf / s_d, fmax(pr_inf, compl_inf(mu_t) / s_c));
+    }
+  };
   int n_eq_ineq, n_bounds;   // uniform counts: rows with multipliers, bound multipliers
 
-  MPCR_D Errors compute_errors(double mu_t) const {
+  MPCR_D Errors compute_errors() const {
     // t = A' lam: contributions of this stage's dynamics rows to (x_k, u_k)
     double A[21], lv[9], out[12];
     for (int k = 0; k < 3; ++k) { A[k] = lin.aX[k]; A[3 + k] = lin.aY[k]; }
@@ -887,7 +897,8 @@ struct WarpSolver {
     const double ydst_n = shfl(on(kDSt) ? yd[kDSt] : 0.0, next_lane());
     const double sig_n_raw = shfl(sigc_prev, next_lane());
     const double sig_n = last ? 0.0 : sig_n_raw;
-    double prinf = 0.0, cmpl = 0.0, sum_y = 0.0, sum_v = 0.0;
+    double prinf = 0.0, pmax = -1.0e300, pmin = 1.0e300, sum_y = 0.0, sum_v = 0.0;
+    double vio = 0.0;      // violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
     if (act) {
       for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(gx[a] + lam[a] - txn[a]));
       dinf = fmax(dinf, fabs(gcost[2] + ydl * gC[2] + yd[kProg] - yprog_n));
@@ -904,6 +915,7 @@ struct WarpSolver {
       }
       for (int a = 0; a < 6; ++a) {
         prinf = fmax(prinf, fabs(dcs[a] * cres[a]));
+        vio = fmax(vio, fabs(cres[a]));
         sum_y += fabs(lam[a] / dcs[a]);
       }
     }
@@ -913,57 +925,40 @@ struct WarpSolver {
       double rs = -yd[r];
       if (row_hasL(r)) {
         rs -= vL[r];
-        cmpl = fmax(cmpl, fabs((s[r] - lo(r)) * vL[r] - mu_t));
+        const double pr_ = (s[r] - lo(r)) * vL[r];
+        pmax = fmax(pmax, pr_);
+        pmin = fmin(pmin, pr_);
         sum_v += fabs(vL[r]);
       }
       if (row_hasU(r)) {
         rs += vU[r];
-        cmpl = fmax(cmpl, fabs((hi(r) - s[r]) * vU[r] - mu_t));
+        const double pr_ = (hi(r) - s[r]) * vU[r];
+        pmax = fmax(pmax, pr_);
+        pmin = fmin(pmin, pr_);
         sum_v += fabs(vU[r]);
       }
       dinf = fmax(dinf, fabs(rs));
       prinf = fmax(prinf, fabs(rd[r]));
       sum_y += fabs(yd[r]);
+      double bl, bh;
+      row_bounds(r, bl, bh);
+      double val = rd[r] + s[r];
+      if (r == kLane) val /= ddl;
+      if (row_hasL(r)) vio = fmax(vio, bl - val);
+      if (row_hasU(r)) vio = fmax(vio, val - bh);
     }
     Errors e;
     e.dual_inf = warp_max(dinf);
     e.pr_inf = warp_max(prinf);
-    e.compl_inf = warp_max(cmpl);
+    e.viol = warp_max(vio);
+    e.prod_max = warp_max(pmax);
+    e.prod_min = warp_min(pmin);
     sum_y = warp_sum(sum_y);
     sum_v = warp_sum(sum_v);
     const double smax = o.s_max;
-    const double s_d = fmax(smax, (sum_y + sum_v) / (double)(n_eq_ineq + n_bounds)) / smax;
-    const double s_c = fmax(smax, sum_v / (double)n_bounds) / smax;
-    e.E = fmax(e.dual_inf / s_d, fmax(e.pr_inf, e.compl_inf / s_c));
+    e.s_d = fmax(smax, (sum_y + sum_v) / (double)(n_eq_ineq + n_bounds)) / smax;
+    e.s_c = fmax(smax, sum_v / (double)n_bounds) / smax;
     return e;
-  }
-
-  // max violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
-  MPCR_D double orig_violation() const {
-    double v = 0.0;
-    if (act)
-      for (int a = 0; a < 6; ++a) v = fmax(v, fabs(cres[a]));
-#pragma unroll 1
-    for (int r = 0; r < kNumRows; ++r) {
-      if (!on(r)) continue;
-      double l, h;
-      row_bounds(r, l, h);
-      double val = rd[r] + s[r];
-      if (r == kLane) val /= ddl;
-      if (row_hasL(r)) v = fmax(v, l - val);
-      if (row_hasU(r)) v = fmax(v, val - h);
-    }
-    return warp_max(v);
-  }
-
-  MPCR_D double theta_local() const {
-    double th = 0.0;
-    if (act)
-      for (int a = 0; a < 6; ++a) th += fabs(dcs[a] * cres[a]);
-#pragma unroll 1
-    for (int r = 0; r < kNumRows; ++r)
-      if (on(r)) th += fabs(rd[r]);
-    return th;
   }
 
   // filter --------------------------------------------------------------------
@@ -980,24 +975,38 @@ struct WarpSolver {
     return a - b <= 10.0 * 2.220446049250313e-16 * fabs(ref);
   }
 
-  // slack steps ds_r = J_r dx + rdv_r (into dsr) and the fraction-to-the-boundary step
-  MPCR_D double slack_steps(const double* rdv) {
+  // slack steps ds_r = J_r dx + rdv_r (into dsr) and the fraction-to-the-boundary step; the same
+  // pass accumulates this lane's share of grad_s(phi)' ds and of theta = |c|_1 + |d - s|_1
+  MPCR_D double slack_steps(const double* rdv, double& gs_ds, double& th_loc) {
     double dup[2], dshp;
     dup[0] = shfl(du[0], prev_lane());
     dup[1] = shfl(du[1], prev_lane());
     double t = shfl(dsh, prev_lane());
     dshp = (lane == 0) ? 0.0 : t;
-    double a = 1.0;
+    double a = 1.0, g = 0.0, th = 0.0;
+    if (act)
+      for (int k = 0; k < 6; ++k) th += fabs(dcs[k] * cres[k]);
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
       double d = 0.0;
       if (on(r)) {
         d = row_lin(r, du, dup, dsh, dshp, dx) + (rdv ? rdv[r] : 0.0);
-        if (row_hasL(r) && d < 0.0) a = fmin(a, -tau * (s[r] - lo(r)) / d);
-        if (row_hasU(r) && d > 0.0) a = fmin(a, tau * (hi(r) - s[r]) / d);
+        th += fabs(rd[r]);
+        if (row_hasL(r)) {
+          const double sl = s[r] - lo(r);
+          if (d < 0.0) a = fmin(a, -tau * sl / d);
+          g += (-mu / sl + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
+        }
+        if (row_hasU(r)) {
+          const double su = hi(r) - s[r];
+          if (d > 0.0) a = fmin(a, tau * su / d);
+          g += (mu / su - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
+        }
       }
       dsr[r] = d;
     }
+    gs_ds = g;
+    th_loc = th;
     return warp_min(a);
   }
 
@@ -1137,46 +1146,41 @@ struct WarpSolver {
         } else {
           if (!cur_finite) { status = kInvalidNumber; break; }
           bool done = false;
-#pragma unroll 1
-          for (int pass = 0;; ++pass) {
-            Errors e = compute_errors(pass == 0 ? 0.0 : mu);
-            if (pass == 0) {
-              const double viol = orig_violation();
-              if (out.trace && lane == 0) {
-                double* tr = out.trace + (size_t)it * kTraceCols;
-                tr[0] = fval / df; tr[1] = e.E; tr[2] = e.pr_inf; tr[3] = e.dual_inf;
-                tr[4] = e.compl_inf; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
-              }
-              if (!finite_d(e.E)) { status = kInvalidNumber; done = true; break; }
-              if (e.E <= o.tol && e.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
-                  e.compl_inf / df <= o.compl_inf_tol) {
-                status = kSolveSucceeded;
-                done = true;
-                break;
-              }
-              if (e.E <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
-                  viol <= o.acceptable_constr_viol_tol &&
-                  e.compl_inf / df <= o.acceptable_compl_inf_tol) {
+          {
+            const Errors e = compute_errors();
+            const double E0 = e.E(0.0), cmp0 = e.compl_inf(0.0);
+            const double viol = e.viol;
+            if (out.trace && lane == 0) {
+              double* tr = out.trace + (size_t)it * kTraceCols;
+              tr[0] = fval / df; tr[1] = E0; tr[2] = e.pr_inf; tr[3] = e.dual_inf;
+              tr[4] = cmp0; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
+            }
+            if (!finite_d(E0)) {
+              status = kInvalidNumber;
+              done = true;
+            } else if (E0 <= o.tol && e.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
+                       cmp0 / df <= o.compl_inf_tol) {
+              status = kSolveSucceeded;
+              done = true;
+            } else {
+              if (E0 <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
+                  viol <= o.acceptable_constr_viol_tol && cmp0 / df <= o.acceptable_compl_inf_tol) {
                 acc_count++;
                 if (acc_count >= o.acceptable_iter) {
                   status = kSolvedToAcceptableLevel;
                   done = true;
-                  break;
                 }
               } else {
                 acc_count = 0;
               }
-              if (it >= o.max_iter) { status = kMaxIterExceeded; done = true; break; }
-            } else {
-              // monotone barrier update (Waechter & Biegler eq. (7))
-              if (e.E <= o.barrier_tol_factor * mu && mu > mu_floor) {
-                mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
-                                         powd(mu, o.mu_superlinear_decrease_power)));
-                tau = fmax(o.tau_min, 1.0 - mu);
-                filt_n = 0;
-              } else {
-                break;
-              }
+              if (!done && it >= o.max_iter) { status = kMaxIterExceeded; done = true; }
+            }
+            // monotone barrier update (Waechter & Biegler eq. (7)); may fire repeatedly
+            while (!done && e.E(mu) <= o.barrier_tol_factor * mu && mu > mu_floor) {
+              mu = fmax(mu_floor, fmin(o.mu_linear_decrease_factor * mu,
+                                       powd(mu, o.mu_superlinear_decrease_power)));
+              tau = fmax(o.tau_min, 1.0 - mu);
+              filt_n = 0;
             }
           }
           if (done) break;
@@ -1207,7 +1211,8 @@ struct WarpSolver {
           dwu = dw;
         }
         if (failed) { status = kErrorInStepComputation; break; }
-        const double a_new = slack_steps(rdv);     // dsr = J_d dx + rdv ; FTB step
+        double gs_ds, th_loc;
+        const double a_new = slack_steps(rdv, gs_ds, th_loc);     // dsr = J_d dx + rdv ; FTB step
         if (phase == kPhInit) {
           // ---- least-squares multipliers: y = -(QP multipliers), yd = (vU - vL) - J_d dx ----
           double ymax = 0.0;
@@ -1238,24 +1243,17 @@ struct WarpSolver {
           last_dw = dw;
           alpha = a_new;
           // grad(phi)' d
-          double g = 0.0;
+          double g = gs_ds;
           {
             const double dup1 = shfl(du[1], prev_lane());
             if (act) {
-              g = gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
-                  gcost[4] * dx[4];
+              g += gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
+                   gcost[4] * dx[4];
               if (lane >= 1) g += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
-            }
-#pragma unroll 1
-            for (int r = 0; r < kNumRows; ++r) {
-              if (!on(r)) continue;
-              double sg, gb;
-              sigma_gsb(r, sg, gb);
-              g += gb * dsr[r];
             }
           }
           gpd = warp_sum(g);
-          theta = warp_sum(theta_local());
+          theta = warp_sum(th_loc);
           phi = fval + mu * barB;
           if (gpd < 0.0) {
             amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
