@@ -203,6 +203,15 @@ enum Phase : int { kPhInit = 0, kPhInit2 = 1, kPhNewton = 2, kPhBacktrack = 3, k
 // ---------------------------------------------------------------------------
 // The solver.  All members are per-lane unless noted "uniform".
 // ---------------------------------------------------------------------------
+// Row (slack) state of one lane.  These arrays are indexed with RUNTIME row numbers (the row loops
+// are deliberately not unrolled), so they live in local memory; keeping them in their own object
+// lets the compiler scalarise every other member of WarpSolver into registers.
+struct RowState {
+  double s[kNumRows], yd[kNumRows], vL[kNumRows], vU[kNumRows];
+  double rd[kNumRows];      // d_r(x) - s_r at the current iterate
+  double dsr[kNumRows];     // slack step of the current direction
+};
+
 template <int MODEL>
 struct WarpSolver {
   const Config& cfg;
@@ -221,13 +230,11 @@ struct WarpSolver {
   double df;                // objective scaling (uniform)
   // slack rows (runtime-indexed -> local memory)
   unsigned rowmask;
-  double s[kNumRows], yd[kNumRows], vL[kNumRows], vU[kNumRows];
-  double rd[kNumRows];      // d_r(x) - s_r at the current iterate
+  RowState& R;              // runtime-indexed row arrays live OUTSIDE this object (see RowState)
   double cres[6];           // x_{k+1} - f(x_k, u_k) at the current iterate
   double fval, barB;        // df * f(x); barrier sum B(s): phi = fval + mu * barB (uniform)
   // search direction
   double dx[6], dsh, du[2];
-  double dsr[kNumRows];
   double mu, tau;
   // filter: one entry per lane
   double filt_th, filt_ph;
@@ -235,9 +242,9 @@ struct WarpSolver {
   int colslot[12];          // packed slot of stage-Hessian entry (r, lane) for lanes 0..11
   double dwflag;            // 1 if diagonal entry (lane, lane) receives delta_w
 
-  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, double* wsbase,
-                    double* stagebase)
-      : cfg(c), p(prm), o(c.o), pb(pv) {
+  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, RowState& rows,
+                    double* wsbase, double* stagebase)
+      : cfg(c), p(prm), o(c.o), pb(pv), R(rows) {
     lane = lane_id();
     N = c.N;
     act = lane < N;
@@ -313,13 +320,13 @@ struct WarpSolver {
   // -------------------------------------------------------------------------
   struct Point {
     double x[6], sh, u[2];
-    double c[6], rd[kNumRows];
+    double c[6];
     double f, theta, barB;  // uniform
     bool finite;            // uniform
   };
 
   // slacks of the point are s + at * dsr (not stored)
-  MPCR_D void eval_point(Point& t, double at) const {
+  MPCR_D void eval_point(Point& t, double* trd /* [kNumRows] out: d_r - s_r */, double at) const {
     double xp[6], shp, up[2];
     gather_prev(t.x, t.sh, t.u, xp, shp, up);
     double f[6];
@@ -346,7 +353,7 @@ struct WarpSolver {
     for (int r = 0; r < kNumRows; ++r) {
       double rdv = 0.0;
       if (on(r)) {
-        const double sv = s[r] + at * dsr[r];
+        const double sv = R.s[r] + at * R.dsr[r];
         rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
         th += fabs(rdv);
         if (row_hasL(r)) {
@@ -362,7 +369,7 @@ struct WarpSolver {
           if (!(su > 0.0)) fin = false;
         }
       }
-      t.rd[r] = rdv;
+      trd[r] = rdv;
     }
     double bar = act ? (-log_d(prod) + o.kappa_d * lin) : 0.0;
     fin = fin && finite_d(fl) && finite_d(th) && finite_d(bar);
@@ -406,7 +413,7 @@ struct WarpSolver {
       hc[6] = df * sc.hvx;
       hc[7] = df * sc.hvy;
       if (cfg.lane_con && on(kLane)) {
-        double yl = yd[kLane] * ddl;     // + yd * Hess(e_C); the Sigma part is a row term
+        double yl = R.yd[kLane] * ddl;     // + yd * Hess(e_C); the Sigma part is a row term
         hc[2] += yl * sc.hC02;
         hc[4] += yl * sc.hC12;
         hc[5] += yl * sc.hC22;
@@ -459,14 +466,14 @@ struct WarpSolver {
     sg = 0.0;
     g = 0.0;
     if (row_hasL(r)) {
-      const double isl = 1.0 / (s[r] - lo(r));
-      sg += vL[r] * isl;
+      const double isl = 1.0 / (R.s[r] - lo(r));
+      sg += R.vL[r] * isl;
       g -= mu * isl;
       if (!row_hasU(r)) g += o.kappa_d * mu;
     }
     if (row_hasU(r)) {
-      const double isu = 1.0 / (hi(r) - s[r]);
-      sg += vU[r] * isu;
+      const double isu = 1.0 / (hi(r) - R.s[r]);
+      sg += R.vU[r] * isu;
       g += mu * isu;
       if (!row_hasL(r)) g -= o.kappa_d * mu;
     }
@@ -490,7 +497,7 @@ struct WarpSolver {
           er = Dr * (rdv ? rdv[r] : 0.0) + g;
         } else {
           Dr = 1.0;
-          er = -((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0));
+          er = -((row_hasU(r) ? R.vU[r] : 0.0) - (row_hasL(r) ? R.vL[r] : 0.0));
         }
       }
       switch (r) {
@@ -888,29 +895,29 @@ struct WarpSolver {
       double t = shfl(out[a], next_lane());
       txn[a] = last ? 0.0 : t;
     }
-    const double ydl = on(kLane) ? yd[kLane] : 0.0;
+    const double ydl = on(kLane) ? R.yd[kLane] : 0.0;
     const double gx[6] = {gcost[0] + ydl * gC[0], gcost[1] + ydl * gC[1], 0.0, gcost[3],
                           gcost[4], 0.0};
-    const double yprog_n_raw = shfl(yd[kProg], next_lane());
+    const double yprog_n_raw = shfl(R.yd[kProg], next_lane());
     const double yprog_n = last ? 0.0 : yprog_n_raw;
-    const double ydthr_n = shfl(on(kDThr) ? yd[kDThr] : 0.0, next_lane());
-    const double ydst_n = shfl(on(kDSt) ? yd[kDSt] : 0.0, next_lane());
+    const double ydthr_n = shfl(on(kDThr) ? R.yd[kDThr] : 0.0, next_lane());
+    const double ydst_n = shfl(on(kDSt) ? R.yd[kDSt] : 0.0, next_lane());
     const double sig_n_raw = shfl(sigc_prev, next_lane());
     const double sig_n = last ? 0.0 : sig_n_raw;
     double prinf = 0.0, pmax = -1.0e300, pmin = 1.0e300, sum_y = 0.0, sum_v = 0.0;
     double vio = 0.0;      // violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
     if (act) {
       for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(gx[a] + lam[a] - txn[a]));
-      dinf = fmax(dinf, fabs(gcost[2] + ydl * gC[2] + yd[kProg] - yprog_n));
-      double ru0 = -out[9] + yd[kThrUb] + yd[kThrLb] + (on(kDThr) ? yd[kDThr] : 0.0) - ydthr_n +
-                   (on(kDThr0) ? yd[kDThr0] : 0.0);
-      double ru1 = -out[10] + yd[kStUb] + yd[kStLb] + (on(kDSt) ? yd[kDSt] : 0.0) - ydst_n +
-                   (on(kDSt0) ? yd[kDSt0] : 0.0) +
+      dinf = fmax(dinf, fabs(gcost[2] + ydl * gC[2] + R.yd[kProg] - yprog_n));
+      double ru0 = -out[9] + R.yd[kThrUb] + R.yd[kThrLb] + (on(kDThr) ? R.yd[kDThr] : 0.0) - ydthr_n +
+                   (on(kDThr0) ? R.yd[kDThr0] : 0.0);
+      double ru1 = -out[10] + R.yd[kStUb] + R.yd[kStLb] + (on(kDSt) ? R.yd[kDSt] : 0.0) - ydst_n +
+                   (on(kDSt0) ? R.yd[kDSt0] : 0.0) +
                    2.0 * p.beta_delta * df * (sigc_prev - sig_n);
       dinf = fmax(dinf, fmax(fabs(ru0), fabs(ru1)));
       if (lane == 0) {
         for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(y0[a] - out[a]));
-        dinf = fmax(dinf, fabs(y0[6] - yd[kProg]));
+        dinf = fmax(dinf, fabs(y0[6] - R.yd[kProg]));
         for (int a = 0; a < 7; ++a) sum_y += fabs(y0[a]);
       }
       for (int a = 0; a < 6; ++a) {
@@ -922,27 +929,27 @@ struct WarpSolver {
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
       if (!on(r)) continue;
-      double rs = -yd[r];
+      double rs = -R.yd[r];
       if (row_hasL(r)) {
-        rs -= vL[r];
-        const double pr_ = (s[r] - lo(r)) * vL[r];
+        rs -= R.vL[r];
+        const double pr_ = (R.s[r] - lo(r)) * R.vL[r];
         pmax = fmax(pmax, pr_);
         pmin = fmin(pmin, pr_);
-        sum_v += fabs(vL[r]);
+        sum_v += fabs(R.vL[r]);
       }
       if (row_hasU(r)) {
-        rs += vU[r];
-        const double pr_ = (hi(r) - s[r]) * vU[r];
+        rs += R.vU[r];
+        const double pr_ = (hi(r) - R.s[r]) * R.vU[r];
         pmax = fmax(pmax, pr_);
         pmin = fmin(pmin, pr_);
-        sum_v += fabs(vU[r]);
+        sum_v += fabs(R.vU[r]);
       }
       dinf = fmax(dinf, fabs(rs));
-      prinf = fmax(prinf, fabs(rd[r]));
-      sum_y += fabs(yd[r]);
+      prinf = fmax(prinf, fabs(R.rd[r]));
+      sum_y += fabs(R.yd[r]);
       double bl, bh;
       row_bounds(r, bl, bh);
-      double val = rd[r] + s[r];
+      double val = R.rd[r] + R.s[r];
       if (r == kLane) val /= ddl;
       if (row_hasL(r)) vio = fmax(vio, bl - val);
       if (row_hasU(r)) vio = fmax(vio, val - bh);
@@ -991,19 +998,19 @@ struct WarpSolver {
       double d = 0.0;
       if (on(r)) {
         d = row_lin(r, du, dup, dsh, dshp, dx) + (rdv ? rdv[r] : 0.0);
-        th += fabs(rd[r]);
+        th += fabs(R.rd[r]);
         if (row_hasL(r)) {
-          const double sl = s[r] - lo(r);
+          const double sl = R.s[r] - lo(r);
           if (d < 0.0) a = fmin(a, -tau * sl / d);
           g += (-mu / sl + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - s[r];
+          const double su = hi(r) - R.s[r];
           if (d > 0.0) a = fmin(a, tau * su / d);
           g += (mu / su - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
       }
-      dsr[r] = d;
+      R.dsr[r] = d;
     }
     gs_ds = g;
     th_loc = th;
@@ -1051,9 +1058,9 @@ struct WarpSolver {
     du[0] = du[1] = 0.0;
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
-      s[r] = 0.0; yd[r] = 0.0; rd[r] = 0.0; dsr[r] = 0.0;
-      vL[r] = (on(r) && row_hasL(r)) ? o.bound_mult_init_val : 0.0;
-      vU[r] = (on(r) && row_hasU(r)) ? o.bound_mult_init_val : 0.0;
+      R.s[r] = 0.0; R.yd[r] = 0.0; R.rd[r] = 0.0; R.dsr[r] = 0.0;
+      R.vL[r] = (on(r) && row_hasL(r)) ? o.bound_mult_init_val : 0.0;
+      R.vU[r] = (on(r) && row_hasU(r)) ? o.bound_mult_init_val : 0.0;
     }
     df = 1.0;
     ddl = 1.0;
@@ -1092,6 +1099,7 @@ struct WarpSolver {
     for (int a = 0; a < 6; ++a) { c_soc[a] = 0.0; sv_dx[a] = 0.0; sv_lam[a] = 0.0; }
     for (int a = 0; a < 7; ++a) sv_y0[a] = 0.0;
     Point tp;
+    double tp_rd[kNumRows];
 
     while (true) {
       // ================= A. derivatives, convergence tests, barrier update ===============
@@ -1190,7 +1198,7 @@ struct WarpSolver {
       // ================= B. linear solve (single call site) ===================================
       if (phase == kPhInit || phase == kPhNewton || phase == kPhSoc) {
         const int mode = (phase == kPhInit) ? 1 : 0;
-        const double* rdv = (phase == kPhInit) ? nullptr : ((phase == kPhSoc) ? d_soc : rd);
+        const double* rdv = (phase == kPhInit) ? nullptr : ((phase == kPhSoc) ? d_soc : R.rd);
         const double* cv = (phase == kPhInit) ? nullptr : ((phase == kPhSoc) ? c_soc : cres);
         double dwu = (phase == kPhInit) ? 1.0 : dw;
         bool first_try = true, ok = false, failed = false;
@@ -1221,8 +1229,8 @@ struct WarpSolver {
 #pragma unroll 1
           for (int r = 0; r < kNumRows; ++r) {
             if (!on(r) || !ok) continue;
-            yd[r] = ((row_hasU(r) ? vU[r] : 0.0) - (row_hasL(r) ? vL[r] : 0.0)) - dsr[r];
-            ymax = fmax(ymax, fabs(yd[r]));
+            R.yd[r] = ((row_hasU(r) ? R.vU[r] : 0.0) - (row_hasL(r) ? R.vL[r] : 0.0)) - R.dsr[r];
+            ymax = fmax(ymax, fabs(R.yd[r]));
           }
           for (int a = 0; a < 7; ++a) { y0[a] = ok ? -newy0[a] : 0.0; ymax = fmax(ymax, fabs(y0[a])); }
           ymax = warp_max(ymax);
@@ -1230,13 +1238,13 @@ struct WarpSolver {
             for (int a = 0; a < 6; ++a) lam[a] = 0.0;
             for (int a = 0; a < 7; ++a) y0[a] = 0.0;
 #pragma unroll 1
-            for (int r = 0; r < kNumRows; ++r) yd[r] = 0.0;
+            for (int r = 0; r < kNumRows; ++r) R.yd[r] = 0.0;
           }
           for (int a = 0; a < 6; ++a) dx[a] = 0.0;     // the init phases evaluate the point itself
           dsh = 0.0;
           du[0] = du[1] = 0.0;
 #pragma unroll 1
-          for (int r = 0; r < kNumRows; ++r) dsr[r] = 0.0;
+          for (int r = 0; r < kNumRows; ++r) R.dsr[r] = 0.0;
           alpha = 0.0;
         } else if (phase == kPhNewton) {
           if (dw > 0.0) dw_last = dw;
@@ -1274,7 +1282,7 @@ struct WarpSolver {
             du[0] = sv_du[0];
             du[1] = sv_du[1];
 #pragma unroll 1
-            for (int r = 0; r < kNumRows; ++r) dsr[r] = sv_dsr[r];
+            for (int r = 0; r < kNumRows; ++r) R.dsr[r] = sv_dsr[r];
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
@@ -1290,15 +1298,15 @@ struct WarpSolver {
         tp.sh = sh + at * dsh;
         tp.u[0] = u[0] + at * du[0];
         tp.u[1] = u[1] + at * du[1];
-        eval_point(tp, at);
+        eval_point(tp, tp_rd, at);
       }
       // ================= D. decisions ===========================================================
       if (phase == kPhInit) {
         // slacks pushed into their (relaxed) bounds; tp.rd holds the row values (s was 0)
 #pragma unroll 1
         for (int r = 0; r < kNumRows; ++r) {
-          if (!on(r)) { s[r] = 0.0; continue; }
-          double v = tp.rd[r];
+          if (!on(r)) { R.s[r] = 0.0; continue; }
+          double v = tp_rd[r];
           const double l = lo(r), h = hi(r);
           double pl, pu;
           if (row_hasL(r) && row_hasU(r)) {
@@ -1310,7 +1318,7 @@ struct WarpSolver {
           }
           if (row_hasL(r)) v = fmax(v, l + pl);
           if (row_hasU(r)) v = fmin(v, h - pu);
-          s[r] = v;
+          R.s[r] = v;
         }
         phase = kPhInit2;
         continue;
@@ -1318,7 +1326,7 @@ struct WarpSolver {
       if (phase == kPhInit2) {
         for (int k = 0; k < 6; ++k) cres[k] = tp.c[k];
 #pragma unroll 1
-        for (int r = 0; r < kNumRows; ++r) rd[r] = tp.rd[r];
+        for (int r = 0; r < kNumRows; ++r) R.rd[r] = tp_rd[r];
         fval = tp.f;
         barB = tp.barB;
         cur_finite = tp.finite;
@@ -1356,7 +1364,7 @@ struct WarpSolver {
             du[0] = sv_du[0];
             du[1] = sv_du[1];
 #pragma unroll 1
-            for (int r = 0; r < kNumRows; ++r) dsr[r] = sv_dsr[r];
+            for (int r = 0; r < kNumRows; ++r) R.dsr[r] = sv_dsr[r];
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
@@ -1364,7 +1372,7 @@ struct WarpSolver {
             th_old = tp.theta;
             for (int a = 0; a < 6; ++a) c_soc[a] = a_soc * c_soc[a] + tp.c[a];
 #pragma unroll 1
-            for (int r = 0; r < kNumRows; ++r) d_soc[r] = a_soc * d_soc[r] + tp.rd[r];
+            for (int r = 0; r < kNumRows; ++r) d_soc[r] = a_soc * d_soc[r] + tp_rd[r];
           }
           continue;
         }
@@ -1384,8 +1392,8 @@ struct WarpSolver {
           sv_du[1] = du[1];
 #pragma unroll 1
           for (int r = 0; r < kNumRows; ++r) {
-            d_soc[r] = alpha * rd[r] + tp.rd[r];
-            sv_dsr[r] = dsr[r];
+            d_soc[r] = alpha * R.rd[r] + tp_rd[r];
+            sv_dsr[r] = R.dsr[r];
           }
           phase = kPhSoc;
           continue;
@@ -1405,17 +1413,17 @@ struct WarpSolver {
         if (!on(r)) continue;
         double sg, gb;
         sigma_gsb(r, sg, gb);
-        const double dyd = (sg + dw) * dsr[r] + gb - yd[r];
-        yd[r] += astep * dyd;
+        const double dyd = (sg + dw) * R.dsr[r] + gb - R.yd[r];
+        R.yd[r] += astep * dyd;
         if (row_hasL(r)) {
-          const double sl = s[r] - lo(r);
-          const double a = mu / sl - vL[r] - vL[r] / sl * dsr[r];
-          if (a < 0.0) az = fmin(az, -tau * vL[r] / a);
+          const double sl = R.s[r] - lo(r);
+          const double a = mu / sl - R.vL[r] - R.vL[r] / sl * R.dsr[r];
+          if (a < 0.0) az = fmin(az, -tau * R.vL[r] / a);
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - s[r];
-          const double b = mu / su - vU[r] + vU[r] / su * dsr[r];
-          if (b < 0.0) az = fmin(az, -tau * vU[r] / b);
+          const double su = hi(r) - R.s[r];
+          const double b = mu / su - R.vU[r] + R.vU[r] / su * R.dsr[r];
+          if (b < 0.0) az = fmin(az, -tau * R.vU[r] / b);
         }
       }
       az = warp_min(az);
@@ -1434,22 +1442,22 @@ struct WarpSolver {
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
         if (!on(r)) continue;
-        const double sold = s[r];
-        const double snew = sold + astep * dsr[r];
+        const double sold = R.s[r];
+        const double snew = sold + astep * R.dsr[r];
         if (row_hasL(r)) {
           const double slo = sold - lo(r), sl = snew - lo(r);
-          const double dv = mu / slo - vL[r] - vL[r] / slo * dsr[r];
-          const double v = vL[r] + az * dv;
-          vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
+          const double dv = mu / slo - R.vL[r] - R.vL[r] / slo * R.dsr[r];
+          const double v = R.vL[r] + az * dv;
+          R.vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
         }
         if (row_hasU(r)) {
           const double suo = hi(r) - sold, su = hi(r) - snew;
-          const double dv = mu / suo - vU[r] + vU[r] / suo * dsr[r];
-          const double v = vU[r] + az * dv;
-          vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
+          const double dv = mu / suo - R.vU[r] + R.vU[r] / suo * R.dsr[r];
+          const double v = R.vU[r] + az * dv;
+          R.vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
         }
-        s[r] = snew;
-        rd[r] = tp.rd[r];
+        R.s[r] = snew;
+        R.rd[r] = tp_rd[r];
       }
       last_alpha = astep;
       it++;
@@ -1490,20 +1498,20 @@ struct WarpSolver {
         if (act) {
           double* l1 = out.lam_g + 7 + lane * bs;     // rows of stage i = lane + 1
           for (int a = 0; a < 6; ++a) l1[a] = lam[a] * idf;
-          l1[6] = yd[kProg] * idf;
-          if (cfg.lane_con) l1[7] = yd[kLane] * ddl * idf;
+          l1[6] = R.yd[kProg] * idf;
+          if (cfg.lane_con) l1[7] = R.yd[kLane] * ddl * idf;
           int off = cfg.wrap ? 6 * lane : (lane == 0 ? 0 : 4 + 6 * (lane - 1));
           double* l2 = out.lam_g + base2 + off;
-          l2[0] = yd[kThrUb] * idf;
-          l2[1] = yd[kThrLb] * idf;
-          l2[2] = yd[kStUb] * idf;
-          l2[3] = yd[kStLb] * idf;
-          if (on(kDThr)) { l2[4] = yd[kDThr] * idf; l2[5] = yd[kDSt] * idf; }
+          l2[0] = R.yd[kThrUb] * idf;
+          l2[1] = R.yd[kThrLb] * idf;
+          l2[2] = R.yd[kStUb] * idf;
+          l2[3] = R.yd[kStLb] * idf;
+          if (on(kDThr)) { l2[4] = R.yd[kDThr] * idf; l2[5] = R.yd[kDSt] * idf; }
           if (lane == 0) {
             double* l3 = out.lam_g + base2 + (cfg.wrap ? 6 * N : 6 * N - 2);
             int q = 0;
-            if (on(kDThr0)) l3[q++] = yd[kDThr0] * idf;
-            if (on(kDSt0)) l3[q++] = yd[kDSt0] * idf;
+            if (on(kDThr0)) l3[q++] = R.yd[kDThr0] * idf;
+            if (on(kDSt0)) l3[q++] = R.yd[kDSt0] * idf;
           }
         }
       }
@@ -1560,7 +1568,8 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     for (int k = lane_id(); k < ls; k += 32) so.lam_g[k] = 0.0;
     syncwarp();
   }
-  WarpSolver<MODEL> solver(cfg, prm, pv, wsbase, stagebase);
+  RowState rows;
+  WarpSolver<MODEL> solver(cfg, prm, pv, rows, wsbase, stagebase);
   solver.solve(so);
 }
 
