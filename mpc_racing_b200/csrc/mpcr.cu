@@ -24,8 +24,11 @@ namespace mpcr {
 
 // STAGE_GLOBAL: the per-stage Riccati storage lives in a per-block global slab (L1/L2
 // resident) instead of shared memory; shared memory then only holds the ~4 KB scratch.
+#ifndef MPCR_MIN_BLOCKS
+#define MPCR_MIN_BLOCKS 1
+#endif
 template <int MODEL, bool STAGE_GLOBAL>
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(32, MPCR_MIN_BLOCKS)
 solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
              int trace_rows, int* __restrict__ counter, double* __restrict__ slabs) {
   extern __shared__ double smem[];
