@@ -33,13 +33,19 @@
 extern "C" {
 #endif
 
-#define MPCR_VERSION 100
+#define MPCR_VERSION 101
 
 /* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
  * models/BlendedBicycleModel.py:23-46 blend of the two) */
 #define MPCR_MODEL_DYNAMIC 0
 #define MPCR_MODEL_KINEMATIC 1
 #define MPCR_MODEL_BLENDED 2
+
+/* solve kernels: one problem per warp (low latency, small batches) or one problem per
+ * lane (throughput, large batches); AUTO picks by batch size */
+#define MPCR_KERNEL_AUTO 0
+#define MPCR_KERNEL_WARP 1
+#define MPCR_KERNEL_LANES 2
 
 /* per-problem status codes */
 #define MPCR_SOLVE_SUCCEEDED 0
@@ -78,6 +84,8 @@ typedef struct mpcr_config {
   double tol, acceptable_tol;
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
   double mu_init;
+  int32_t solve_kernel;      /* MPCR_KERNEL_* (0 = auto) */
+  int32_t reserved_;
 } mpcr_config;
 
 typedef struct mpcr_handle mpcr_handle;
@@ -124,7 +132,8 @@ int mpcr_solve_batch_trace(mpcr_handle* h, int B, const double* x0, const double
 /* Device time of the last solve kernel launch in milliseconds (CUDA events on
  * the launch stream); blocks until that launch has finished. */
 int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
-/* Launch geometry of the solve kernel: blocks, warps per block, dynamic shared bytes. */
+/* Launch geometry of the last solve launch (or of the warp kernel before any launch):
+ * blocks, warps per block, dynamic shared bytes. */
 int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem_bytes);
 
 /* ---- track geometry (replaces splines/ParameterizedLine.py:19-105 and

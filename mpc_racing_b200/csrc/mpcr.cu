@@ -18,6 +18,7 @@
 
 #include "mpcr_config.h"
 #include "mpcr_ipm.cuh"
+#include "mpcr_ipm_lanes.cuh"
 #include "mpcr_track.cuh"
 
 namespace mpcr {
@@ -57,6 +58,27 @@ static SolveKernelFn pick_kernel(int model, bool stage_global) {
   return solve_kernel<kBlended, false>;
 }
 
+// Throughput kernel: one problem per LANE (mpcr_ipm_lanes.cuh).  Block = one warp; warp w owns
+// the workspace slab [w * ws_doubles * 32, ...) laid out [element][lane] (coalesced).
+template <int MODEL>
+__global__ void __launch_bounds__(32, 1)
+lane_solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
+                  int trace_rows, double* __restrict__ ws, int ws_doubles) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 32 + lane;
+  if (b >= B) return;
+  double* w = ws + (size_t)blockIdx.x * ws_doubles * 32 + lane;
+  lane_solve_problem<MODEL>(cfg, in, out, b, trace_rows, w);
+}
+
+typedef void (*LaneKernelFn)(const Config, const BatchIn, const BatchOut, int, int, double*, int);
+
+static LaneKernelFn pick_lane_kernel(int model) {
+  if (model == kDynamic) return lane_solve_kernel<kDynamic>;
+  if (model == kKinematic) return lane_solve_kernel<kKinematic>;
+  return lane_solve_kernel<kBlended>;
+}
+
 // DFMA-chain microbenchmark: the measured fp64 roofline denominator
 // (MEASURED_PEAKS.json has no fp64 entry).  8 independent chains per thread.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
@@ -85,6 +107,16 @@ struct mpcr_handle {
   double* d_slabs = nullptr;
   bool stage_global = false;
   SolveKernelFn kernel = nullptr;
+  LaneKernelFn lane_kernel = nullptr;
+  int kernel_sel = MPCR_KERNEL_AUTO;     // config / MPCR_KERNEL env
+  // AUTO: batches at least this large use the lane kernel.  Measured on B200 (profiles/r1e_*):
+  // at B = 16384 the lane kernel is 4x SLOWER than the warp kernel (16k threads cannot hide the
+  // HBM latency of its global-memory workspace), so AUTO never selects it unless the
+  // MPCR_LANES_MIN_BATCH environment variable lowers this threshold.
+  int lanes_min_batch = 1 << 30;
+  double* d_lane_ws = nullptr;           // lane-kernel workspace, grown on demand
+  size_t lane_ws_warps = 0;
+  int last_blocks = 0, last_smem = 0;    // geometry of the last launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // staging buffers for the host-pointer path
@@ -132,6 +164,16 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
     h->stage_global = e ? (atoi(e) != 0) : false;
   }
   h->kernel = pick_kernel(h->cfg.model, h->stage_global);
+  h->lane_kernel = pick_lane_kernel(h->cfg.model);
+  h->kernel_sel = cfg->solve_kernel;
+  {
+    const char* e = getenv("MPCR_KERNEL");
+    if (e && !strcmp(e, "warp")) h->kernel_sel = MPCR_KERNEL_WARP;
+    if (e && !strcmp(e, "lanes")) h->kernel_sel = MPCR_KERNEL_LANES;
+    const char* m = getenv("MPCR_LANES_MIN_BATCH");
+    if (m && atoi(m) > 0) h->lanes_min_batch = atoi(m);
+  }
+  CK(cudaFuncSetAttribute(h->lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   h->smem_bytes = (h->stage_global ? kScratch : ws_doubles(h->cfg.N)) * (int)sizeof(double);
   CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   if (!h->stage_global)
@@ -161,6 +203,7 @@ extern "C" int mpcr_destroy(mpcr_handle* h) {
   cudaSetDevice(h->device);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_slabs) cudaFree(h->d_slabs);
+  if (h->d_lane_ws) cudaFree(h->d_lane_ws);
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->d_ibuf) cudaFree(h->d_ibuf);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -176,9 +219,9 @@ extern "C" int mpcr_lam_g_stride(mpcr_handle* h) {
 
 extern "C" int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem) {
   if (!h) return MPCR_ERR_INVALID_ARG;
-  if (blocks) *blocks = h->num_sms * h->blocks_per_sm;
+  if (blocks) *blocks = h->last_blocks ? h->last_blocks : h->num_sms * h->blocks_per_sm;
   if (warps_per_block) *warps_per_block = 1;
-  if (smem) *smem = h->smem_bytes;
+  if (smem) *smem = h->last_blocks ? h->last_smem : h->smem_bytes;
   return MPCR_OK;
 }
 
@@ -193,8 +236,31 @@ extern "C" int mpcr_last_kernel_ms(mpcr_handle* h, float* ms) {
 
 static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut& out,
                         int trace_rows, cudaStream_t st) {
+  const bool lanes = h->kernel_sel == MPCR_KERNEL_LANES ||
+                     (h->kernel_sel == MPCR_KERNEL_AUTO && B >= h->lanes_min_batch);
+  if (lanes) {
+    const size_t warps = ((size_t)B + 31) / 32;
+    const int wsd = lane_ws_doubles(h->cfg.N);
+    if (warps > h->lane_ws_warps) {
+      if (h->d_lane_ws) cudaFree(h->d_lane_ws);
+      h->d_lane_ws = nullptr;
+      h->lane_ws_warps = 0;
+      CK(cudaMalloc(&h->d_lane_ws, warps * (size_t)wsd * 32 * sizeof(double)));
+      h->lane_ws_warps = warps;
+    }
+    CK(cudaEventRecord(h->ev0, st));
+    h->lane_kernel<<<(unsigned)warps, 32, 0, st>>>(h->cfg, in, out, B, trace_rows, h->d_lane_ws, wsd);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    h->last_blocks = (int)warps;
+    h->last_smem = 0;
+    return MPCR_OK;
+  }
   int grid = h->num_sms * h->blocks_per_sm;
   if (grid > B) grid = B;
+  h->last_blocks = grid;
+  h->last_smem = h->smem_bytes;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   CK(cudaEventRecord(h->ev0, st));
   h->kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, h->d_slabs);

@@ -40,6 +40,8 @@ inline void config_default(mpcr_config* c) {
   c->constr_viol_tol = 1e-4;
   c->compl_inf_tol = 1e-4;
   c->mu_init = 0.1;
+  c->solve_kernel = MPCR_KERNEL_AUTO;
+  c->reserved_ = 0;
 }
 
 inline void config_convert(const mpcr_config& c, Config* out) {
@@ -120,6 +122,7 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.model < 0 || c.model > 2) { *why = "unknown model"; return false; }
   if (c.max_iter < 0) { *why = "max_iter must be >= 0"; return false; }
   if (c.n_exp < 1.0) { *why = "n_exp must be >= 1"; return false; }
+  if (c.solve_kernel < 0 || c.solve_kernel > 2) { *why = "unknown solve_kernel"; return false; }
   return true;
 }
 

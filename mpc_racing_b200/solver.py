@@ -50,7 +50,8 @@ class BatchedMPC:
                  fixed_params: Optional[FixedControllerParameters] = None,
                  runtime_params: Optional[RuntimeControllerParameters] = None,
                  wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
-                 tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False):
+                 tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False,
+                 solve_kernel=0):
         self.lib = _capi.load_library()
         fp = fixed_params or FixedControllerParameters()
         rp = runtime_params or RuntimeControllerParameters()
@@ -75,6 +76,8 @@ class BatchedMPC:
         cfg.d_max = float(rp.d_max if honor_instance_d_max else RuntimeControllerParameters.d_max)
         cfg.tol = float(tol)
         cfg.acceptable_tol = float(acceptable_tol)
+        # 0 = auto (by batch size), 1 = one problem per warp, 2 = one problem per lane
+        cfg.solve_kernel = int({"auto": 0, "warp": 1, "lanes": 2}.get(solve_kernel, solve_kernel))
         self.cfg = cfg
         self.N = cfg.N
         self.on_device = bool(on_device)

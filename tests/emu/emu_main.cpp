@@ -7,6 +7,7 @@
 
 #include "../../mpc_racing_b200/csrc/mpcr_config.h"
 #include "../../mpc_racing_b200/csrc/mpcr_ipm.cuh"
+#include "../../mpc_racing_b200/csrc/mpcr_ipm_lanes.cuh"
 
 namespace {
 struct Job {
@@ -48,6 +49,25 @@ extern "C" int emu_solve_batch(const mpcr_config* c, int B, const double* x0, co
     Job j{&cfg, &in, &out, b, cfg.o.max_iter + 1, ws.data()};
     emu::run_warp(lane_body, &j);
   }
+  return 0;
+}
+
+// lane-per-problem solver (mpcr_ipm_lanes.cuh): plain sequential code on the host (stride 1)
+extern "C" int emu_solve_batch_lanes(const mpcr_config* c, int B, const double* x0, const double* u_prev,
+                                     const double* s0, const double* cx, const double* cy,
+                                     const double* max_err, const double* params, const double* u_warm,
+                                     double* U, double* X, double* S, double* eC, double* eL,
+                                     double* lam_g, double* obj, int32_t* status, int32_t* iters,
+                                     double* trace) {
+  const char* why = nullptr;
+  if (!mpcr::config_valid(*c, &why)) return -1;
+  mpcr::Config cfg;
+  mpcr::config_convert(*c, &cfg);
+  mpcr::BatchIn in{x0, u_prev, s0, cx, cy, max_err, params, u_warm};
+  mpcr::BatchOut out{U, X, S, eC, eL, lam_g, obj, status, iters, trace};
+  std::vector<double> ws(mpcr::lane_ws_doubles(cfg.N));
+  for (int b = 0; b < B; ++b)
+    mpcr::lane_solve_problem_any(cfg, in, out, b, cfg.o.max_iter + 1, ws.data());
   return 0;
 }
 

@@ -162,3 +162,24 @@ def test_dropin_mpc_class(cfg2):
     ref1 = oracle_solve(d['x0'][0], d['u_prev'][0], 69.6, d['cx'][0], d['cy'][0], N=25, Ts=0.1)
     assert (s1 is None) == (ref1['status'] < 0)
     assert r1[0].shape == (6, 26) and np.isfinite(r1[0]).all()
+
+
+def test_lane_kernel_matches_warp_kernel_and_oracle(cfg2):
+    """The throughput kernel (one problem per lane, mpcr_ipm_lanes.cuh) against the warp kernel on a
+    ragged batch (not a multiple of 32) and against the oracle on a few problems."""
+    from mpc_racing_b200.solver import BatchedMPC
+    idx = list(range(1000, 1000 + 203))
+    args = (cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx])
+    a = BatchedMPC(N=30, Ts=0.05, solve_kernel="warp").solve(*args)
+    lanes = BatchedMPC(N=30, Ts=0.05, solve_kernel="lanes")
+    b = lanes.solve(*args)
+    assert lanes.launch_info()["blocks"] == (len(idx) + 31) // 32
+    assert (a.status == b.status).all()
+    same = a.iters == b.iters
+    assert same.mean() >= 0.9
+    assert (np.abs(a.obj - b.obj) / np.abs(a.obj))[same].max() <= 1e-8
+    res = _asdict(b)
+    for j in (0, 77, 202):
+        k = idx[j]
+        ref = oracle_solve(cfg2['x0'][k], cfg2['u_prev'][k], cfg2['s0'][k], cfg2['cx'][k], cfg2['cy'][k])
+        assert_parity(res, j, ref)

@@ -1,0 +1,69 @@
+"""Lane-per-problem solver (mpc_racing_b200/csrc/mpcr_ipm_lanes.cuh), compiled for the host by
+tests/emu (test infrastructure), against the numpy oracle and against the emulated
+warp-per-problem solver on seeded inputs.  The CUDA build of the same source is
+checked on the GPU in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from emu_util import emu_solve
+from mpc_racing_b200.workload import load_fixture
+from oracle import vehicle as V
+from parity_util import assert_parity, oracle_solve
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    return load_fixture("cfg2_shanghai_4096.npz")
+
+
+def test_lanes_vs_oracle_default_horizon(cfg2):
+    idx = list(range(8, 14))
+    out = emu_solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx],
+                    lanes=True)
+    for j, b in enumerate(idx):
+        ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b])
+        assert_parity(out, j, ref)
+
+
+def test_lanes_follow_the_warp_solver_iteration_by_iteration(cfg2):
+    """Same algorithm, different mapping: traces agree to round-off while the paths coincide."""
+    idx = list(range(64, 96))
+    args = (cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx])
+    a = emu_solve(*args, trace=True)
+    b = emu_solve(*args, trace=True, lanes=True)
+    assert (a['status'] == b['status']).all()
+    same = a['iters'] == b['iters']
+    assert same.mean() >= 0.9
+    assert (np.abs(a['obj'] - b['obj']) / np.abs(a['obj']))[same].max() <= 1e-8
+    for j in np.where(same)[0][:8]:
+        n = min(10, int(a['iters'][j]))
+        ta, tb = a['trace'][j, :n], b['trace'][j, :n]
+        assert np.allclose(ta, tb, rtol=1e-6, atol=1e-9), (j, np.abs(ta - tb).max())
+
+
+def test_lanes_variants(cfg2):
+    d3 = load_fixture("cfg3_t1_triple_512.npz")
+    out = emu_solve(d3['x0'][[0]], d3['u_prev'][[0]], d3['s0'][[0]], d3['cx'][[0]], d3['cy'][[0]],
+                    max_err=d3['max_err'][[0]], lane_constraint=1, lanes=True)
+    ref = oracle_solve(d3['x0'][0], d3['u_prev'][0], d3['s0'][0], d3['cx'][0], d3['cy'][0], lane=True,
+                       max_error=float(d3['max_err'][0]))
+    assert_parity(out, 0, ref)
+    # production horizon, no wrap rows, kinematic model, warm start without a previous input
+    dp = load_fixture("prod_t4_256.npz")
+    out = emu_solve(dp['x0'][[1]], dp['u_prev'][[1]], dp['s0'][[1]], dp['cx'][[1]], dp['cy'][[1]], N=15, lanes=True)
+    assert_parity(out, 0, oracle_solve(dp['x0'][1], dp['u_prev'][1], dp['s0'][1], dp['cx'][1], dp['cy'][1], N=15))
+    i = [3]
+    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i],
+                    wrap_constraint=0, lanes=True)
+    assert_parity(out, 0, oracle_solve(cfg2['x0'][3], cfg2['u_prev'][3], cfg2['s0'][3], cfg2['cx'][3],
+                                       cfg2['cy'][3], wrap=False))
+    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], model=1,
+                    lanes=True)
+    assert_parity(out, 0, oracle_solve(cfg2['x0'][3], cfg2['u_prev'][3], cfg2['s0'][3], cfg2['cx'][3],
+                                       cfg2['cy'][3], model=V.MODEL_KINEMATIC))
+    cold = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], lanes=True)
+    nan = np.full((1, 2), np.nan)
+    out = emu_solve(cfg2['x0'][i], nan, cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], u_warm=cold['U'].copy(),
+                    lanes=True)
+    assert_parity(out, 0, oracle_solve(cfg2['x0'][3], None, cfg2['s0'][3], cfg2['cx'][3], cfg2['cy'][3],
+                                       u_warm=cold['U'][0]))
