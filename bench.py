@@ -102,7 +102,7 @@ def run_reference(args):
         return
     from mpc_racing_b200.workload import make_batch
     cores = os.cpu_count() or 1
-    per_step = max(2 * cores, 16)
+    per_step = max(4 * cores, 32)
     batch = make_batch(per_step * (args.steps + args.warmup))
     from multiprocessing import get_context
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -212,6 +212,22 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_conv = int((hres.status >= 0).sum())
+    # ---- p50 single-solve latency (BASELINE.json metric, second half): B = 1 through the C ABI
+    #      with host buffers, H2D + kernel + D2H inside each timed call (rank 0 only)
+    lat = None
+    if rank == 0:
+        one = {k: pin[k][:1] for k in pin}
+        o1 = hsolver.alloc_host_outputs(1, want_lam_g=True, pinned=True)
+        ts = []
+        for i in range(60):
+            j = i % min(B, 50)
+            one = {k: pin[k][j:j + 1] for k in pin}
+            t1 = time.perf_counter()
+            hsolver.solve(one["x0"], one["u_prev"], one["s0"], one["cx"], one["cy"], out=o1)
+            ts.append(time.perf_counter() - t1)
+        ts = np.array(ts[10:]) * 1e3
+        lat = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)),
+               "batch": 1, "calls": int(ts.size), "includes": "H2D + solve kernel + D2H, host pointers"}
     h2d = sum(pin[k].nbytes for k in pin)
     d2h = sum(v.nbytes for v in hout.values() if v is not None)
     stop.set()
@@ -246,7 +262,7 @@ def run_gpu(args):
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            nprob = max(2 * cores, 32)
+            nprob = max(8 * cores, 64)          # ~10-20 s of CPU work on the box's host cores
             rate, conv, dt = cpu_pool_rate(host, nprob, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {nprob} problems of rank 0's batch, oracle/ipm.py (numpy port of "
@@ -273,6 +289,7 @@ def run_gpu(args):
                                  "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_launch": bytes_alg}},
             "cpu_baseline": cpu,
+            "single_solve_latency": lat,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
