@@ -169,6 +169,18 @@ int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, double lookah
 int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x, const double* u, double dt,
                     double* x_out, void* cuda_stream);
 
+/* ---- vehicle-model step with analytic derivatives (replaces CasADi's AD of
+ * control/MPC.py:186-260 f_vehicle / f_vehicle_kinematic and of the blend of
+ * models/BlendedBicycleModel.py:23-46): f[B,6] = x+, jac[B,6,8] = d x+/d(x,u) (or NULL),
+ * hess[B,8,8] = sum_k lam[b,k] d2 x+_k/d(x,u)^2 (or NULL; needs lam[B,6]).
+ * integrator: MPCR_INTEGRATOR_EULER = the explicit-Euler maps the reference's NLP uses,
+ * MPCR_INTEGRATOR_RK4 = classical RK4 of the same vector field (extension, north-star item 2). */
+#define MPCR_INTEGRATOR_EULER 0
+#define MPCR_INTEGRATOR_RK4 1
+int mpcr_model_eval(mpcr_handle* h, int model, int integrator, int B, const double* x, const double* u,
+                    double Ts, const double* lam, double* f, double* jac, double* hess,
+                    void* cuda_stream);
+
 /* Measured fp64 FMA peak of the device (DFMA-chain microbenchmark, TFLOP/s):
  * the roofline denominator for the solve kernel. */
 int mpcr_fp64_peak_tflops(mpcr_handle* h, double* tflops);

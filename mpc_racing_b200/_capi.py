@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
     "mpcr_launch_info", "mpcr_fp64_peak_tflops",
     "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
-    "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step",
+    "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step", "mpcr_model_eval",
 ]
 
 _lib = None
@@ -101,6 +101,8 @@ def load_library(path=None):
     lib.mpcr_track_lookup_error.restype = C.c_int
     lib.mpcr_plant_step.argtypes = [V, C.c_int, C.c_int, V, V, C.c_double, V, V]
     lib.mpcr_plant_step.restype = C.c_int
+    lib.mpcr_model_eval.argtypes = [V, C.c_int, C.c_int, C.c_int, V, V, C.c_double, V, V, V, V, V]
+    lib.mpcr_model_eval.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

@@ -736,3 +736,72 @@ extern "C" int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x
   if (e != cudaSuccess) { h->err = std::string("mpcr_plant_step: ") + cudaGetErrorString(e); return MPCR_ERR_CUDA; }
   return MPCR_OK;
 }
+
+// =====================================================================================
+// Model step with analytic Jacobian / Hessian, Euler or RK4 (mpcr_rk4.cuh): one thread per query
+// =====================================================================================
+#include "mpcr_rk4.cuh"
+
+namespace mpcr {
+__global__ void __launch_bounds__(64) model_eval_kernel(int model, int integrator, int B,
+                                                        const double* __restrict__ x,
+                                                        const double* __restrict__ u, double Ts,
+                                                        const double* __restrict__ lam,
+                                                        double* __restrict__ f, double* __restrict__ jac,
+                                                        double* __restrict__ hess) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    double xi[6], ui[2], li[6], fo[6], J[48], H[64];
+    for (int k = 0; k < 6; ++k) { xi[k] = x[(size_t)b * 6 + k]; li[k] = lam ? lam[(size_t)b * 6 + k] : 0.0; }
+    ui[0] = u[(size_t)b * 2];
+    ui[1] = u[(size_t)b * 2 + 1];
+    model_eval_dense(model, integrator, xi, ui, Ts, lam ? li : nullptr, fo, jac ? J : nullptr,
+                     (hess && lam) ? H : nullptr);
+    for (int k = 0; k < 6; ++k) f[(size_t)b * 6 + k] = fo[k];
+    if (jac)
+      for (int k = 0; k < 48; ++k) jac[(size_t)b * 48 + k] = J[k];
+    if (hess)
+      for (int k = 0; k < 64; ++k) hess[(size_t)b * 64 + k] = lam ? H[k] : 0.0;
+  }
+}
+}  // namespace mpcr
+
+extern "C" int mpcr_model_eval(mpcr_handle* h, int model, int integrator, int B, const double* x,
+                               const double* u, double Ts, const double* lam, double* f, double* jac,
+                               double* hess, void* stream) {
+  if (!h || !x || !u || !f || B < 0 || model < 0 || model > 2 || integrator < 0 || integrator > 1 ||
+      !(Ts > 0.0) || (hess && !lam)) {
+    if (h) h->err = "mpcr_model_eval: invalid argument";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  if (B == 0) return MPCR_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 64;
+  int blocks = (B + threads - 1) / threads;
+  if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+  if (h->pub.pointers_on_device) {
+    model_eval_kernel<<<blocks, threads, 0, st>>>(model, integrator, B, x, u, Ts, lam, f, jac, hess);
+    CK(cudaGetLastError());
+    return MPCR_OK;
+  }
+  double* d = nullptr;
+  const size_t nin = (size_t)B * 14, nout = (size_t)B * (6 + 48 + 64);
+  CK(cudaMalloc(&d, (nin + nout) * sizeof(double)));
+  double *dx = d, *du = d + (size_t)B * 6, *dl = du + (size_t)B * 2, *df = d + nin, *dj = df + (size_t)B * 6,
+         *dh = dj + (size_t)B * 48;
+  cudaError_t e = cudaMemcpyAsync(dx, x, (size_t)B * 6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(du, u, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && lam) e = cudaMemcpyAsync(dl, lam, (size_t)B * 6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    model_eval_kernel<<<blocks, threads, 0, st>>>(model, integrator, B, dx, du, Ts, lam ? dl : nullptr, df,
+                                                  jac ? dj : nullptr, hess ? dh : nullptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f, df, (size_t)B * 6 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && jac) e = cudaMemcpyAsync(jac, dj, (size_t)B * 48 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && hess) e = cudaMemcpyAsync(hess, dh, (size_t)B * 64 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { h->err = std::string("mpcr_model_eval: ") + cudaGetErrorString(e); return MPCR_ERR_CUDA; }
+  return MPCR_OK;
+}

@@ -121,6 +121,28 @@ class BatchedMPC:
         return ms.value
 
     # ------------------------------------------------------------------
+    def model_eval(self, x, u, lam=None, model=None, integrator="euler", Ts=None, jac=True, hess=True):
+        """Vehicle-model step x+ with analytic Jacobian [B,6,8] over (x, u) and lam-weighted Hessian
+        [B,8,8] (host arrays).  integrator "euler" = the maps of control/MPC.py:186-260 that the
+        reference's NLP uses; "rk4" = classical RK4 of the same vector field (extension)."""
+        assert not self.on_device, "model_eval takes host arrays"
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        B = x.shape[0]
+        assert x.shape == (B, 6) and u.shape == (B, 2)
+        lam = None if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
+        m = self.cfg.model if model is None else (MODEL_IDS[model] if isinstance(model, str) else int(model))
+        integ = {"euler": 0, "rk4": 1}.get(integrator, integrator)
+        f = np.empty((B, 6))
+        J = np.empty((B, 6, 8)) if jac else None
+        H = np.empty((B, 8, 8)) if (hess and lam is not None) else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        self._check(self.lib.mpcr_model_eval(self._h, m, int(integ), B, ptr(x), ptr(u),
+                                             float(self.cfg.Ts if Ts is None else Ts), ptr(lam), ptr(f),
+                                             ptr(J), ptr(H), None))
+        return f, J, H
+
+    # ------------------------------------------------------------------
     def solve(self, x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None,
               want_lam_g=True, trace=False, stream=None, out=None) -> BatchResult:
         if self.on_device:

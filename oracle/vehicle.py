@@ -367,3 +367,65 @@ def blended_derivs(x, u, Ts, lam=None):
 
 def model_derivs(model, x, u, Ts, lam=None):
     return (dynamic_derivs, kinematic_derivs, blended_derivs)[model](x, u, Ts, lam)
+
+
+# ---------------------------------------------------------------------------
+# RK4 discretisation (extension; the reference's NLP uses the explicit-Euler maps above,
+# control/MPC.py:186-260).  The vector field is the model's Euler increment per unit time,
+# g(y, u) = (F(y, u; Ts) - y) / Ts: for the dynamic single-track model this is the ODE
+# right-hand side itself, for the kinematic / blended maps (which assign v_y, r algebraically)
+# it is the relaxation field those maps define.  With D_i = F(y_i, u) - y_i:
+#     y_1 = x, y_2 = x + D_1/2, y_3 = x + D_2/2, y_4 = x + D_3,
+#     x+  = x + (D_1 + 2 D_2 + 2 D_3 + D_4) / 6.
+# ---------------------------------------------------------------------------
+_RK4_W = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+_RK4_C = (0.0, 0.5, 0.5, 1.0)
+
+
+def rk4_step(model, x, u, Ts):
+    x = np.asarray(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    acc = np.zeros_like(x)
+    d = np.zeros_like(x)
+    for i in range(4):
+        y = x + _RK4_C[i] * d
+        d = f_model(model, y, u, Ts) - y
+        acc = acc + _RK4_W[i] * d
+    return x + acc
+
+
+def rk4_derivs(model, x, u, Ts, lam=None):
+    """Jacobian (6,8) of rk4_step over z = (x, u) and, if ``lam`` is given, the lam-weighted
+    Hessian (8,8): forward sensitivities of the four stage points, adjoint stage weights
+    mu_i, H = sum_i W_i' Hess(mu_i' D)(y_i, u) W_i."""
+    x = np.asarray(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    I0 = np.hstack([np.eye(6), np.zeros((6, 2))])
+    E = np.hstack([np.zeros((2, 6)), np.eye(2)])
+    ys, Ds, Ws = [], [], []
+    d = np.zeros(6)
+    S = np.zeros((6, 8))
+    J = I0.copy()
+    for i in range(4):
+        y = x + _RK4_C[i] * d
+        Y = I0 + _RK4_C[i] * S
+        jac, _ = model_derivs(model, y, u, Ts, None)
+        D = jac - I0
+        W = np.vstack([Y, E])
+        d = f_model(model, y, u, Ts) - y
+        S = D @ W
+        J = J + _RK4_W[i] * S
+        ys.append(y); Ds.append(D); Ws.append(W)
+    if lam is None:
+        return J, None
+    lam = np.asarray(lam, dtype=np.float64)
+    H = np.zeros((8, 8))
+    mu_next = None
+    for i in (3, 2, 1, 0):
+        mu = _RK4_W[i] * lam
+        if i < 3:
+            mu = mu + _RK4_C[i + 1] * (Ds[i + 1][:, :6].T @ mu_next)
+        _, Hi = model_derivs(model, ys[i], u, Ts, mu)
+        H += Ws[i].T @ Hi @ Ws[i]
+        mu_next = mu
+    return J, H

@@ -83,6 +83,15 @@ extern "C" void emu_model_lin(int model, const double* x, const double* u, doubl
     for (int k = 0; k < 2; ++k) lin21[15 + 2 * i + k] = L.bu[i][k];
 }
 
+// Euler / RK4 model evaluation with dense Jacobian (6x8) and lam-weighted Hessian (8x8)
+#include "../../mpc_racing_b200/csrc/mpcr_rk4.cuh"
+extern "C" void emu_model_eval(int model, int integrator, int B, const double* x, const double* u,
+                               double Ts, const double* lam, double* f, double* jac, double* hess) {
+  for (int b = 0; b < B; ++b)
+    mpcr::model_eval_dense(model, integrator, x + 6 * b, u + 2 * b, Ts, lam ? lam + 6 * b : nullptr,
+                           f + 6 * b, jac ? jac + 48 * b : nullptr, hess ? hess + 64 * b : nullptr);
+}
+
 // ---- track geometry: the same host/device functions the CUDA track kernels call ------------
 #include "../../mpc_racing_b200/csrc/mpcr_track.cuh"
 

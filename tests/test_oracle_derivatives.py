@@ -74,3 +74,38 @@ def test_vectorised_matches_scalar():
         Jk, Hk = V.dynamic_derivs(x[k], u[k], 0.05, lam[k])
         np.testing.assert_array_equal(J[k], Jk)
         np.testing.assert_array_equal(H[k], Hk)
+
+
+def _torch_rk4(model, z, Ts):
+    x, u = z[:6], z[6:]
+    acc = torch.zeros(6, dtype=torch.float64)
+    d = torch.zeros(6, dtype=torch.float64)
+    for c, w in ((0.0, 1 / 6), (0.5, 1 / 3), (0.5, 1 / 3), (1.0, 1 / 6)):
+        y = x + c * d
+        d = _torch_model(model, torch.cat([y, u]), Ts) - y
+        acc = acc + w * d
+    return x + acc
+
+
+@pytest.mark.parametrize("model", [V.MODEL_DYNAMIC, V.MODEL_KINEMATIC, V.MODEL_BLENDED])
+def test_rk4_value_jac_hess(model):
+    """RK4 extension (north star item 2): value, Jacobian and lam-weighted Hessian of the RK4 map
+    built from the Euler-map derivatives, against torch.autograd through the composed map."""
+    rng = np.random.default_rng(3)
+    for trial in range(8):
+        x = np.array([rng.uniform(-100, 100), rng.uniform(-100, 100), rng.uniform(-3, 3),
+                      rng.uniform(16, 40) if trial % 2 else rng.uniform(3, 13),
+                      rng.normal(0, 1.0), rng.normal(0, 0.3)])
+        u = np.array([rng.uniform(-1, 0.85), rng.uniform(-0.9, 0.9)])
+        lam = rng.normal(0, 1, 6)
+        Ts = 0.05 if trial % 2 else 0.1
+        z = torch.tensor(np.concatenate([x, u]), dtype=torch.float64)
+        f_t = _torch_rk4(model, z, Ts).numpy()
+        J_t = torch.autograd.functional.jacobian(lambda zz: _torch_rk4(model, zz, Ts), z).numpy()
+        lam_t = torch.tensor(lam)
+        H_t = torch.autograd.functional.hessian(lambda zz: (lam_t * _torch_rk4(model, zz, Ts)).sum(), z).numpy()
+        f_o = V.rk4_step(model, x, u, Ts)
+        J_o, H_o = V.rk4_derivs(model, x, u, Ts, lam)
+        np.testing.assert_allclose(f_o, f_t, rtol=1e-13, atol=1e-12)
+        np.testing.assert_allclose(J_o, J_t, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(H_o, H_t, rtol=1e-8, atol=1e-9)
