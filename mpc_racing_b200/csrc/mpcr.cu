@@ -40,7 +40,7 @@ solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOu
     if (lane == 0) b = atomicAdd(counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
-    solve_problem<MODEL>(cfg, in, out, b, trace_rows, smem, stage);
+    solve_problem<MODEL, STAGE_GLOBAL>(cfg, in, out, b, trace_rows, smem, stage);
     __syncwarp();
   }
 }
@@ -176,9 +176,12 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   CK(cudaFuncSetAttribute(h->lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   h->smem_bytes = (h->stage_global ? kScratch : ws_doubles(h->cfg.N)) * (int)sizeof(double);
   CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  if (!h->stage_global)
-    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
+  if (!h->stage_global) {
+    int carve = cudaSharedmemCarveoutMaxShared;
+    const char* e = getenv("MPCR_CARVEOUT");      // percent of the unified L1/shared array
+    if (e && atoi(e) > 0 && atoi(e) <= 100) carve = atoi(e);
+    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, 32,
                                                    h->smem_bytes));
   if (h->blocks_per_sm < 1) {

@@ -89,32 +89,36 @@ constexpr int kScratch = 81 + 108 + 144 + 27 + 27 + 36 + kMisc;
 MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
 MPCR_HD int stage_doubles(int N) { return (N + 1) * kStride; }
 
+// SG (stage-global): the per-stage storage lives in a global slab instead of shared memory.
+// On the device every shared-memory pointer is re-derived from the dynamic shared array at the
+// point of use, so that the compiler knows the address space and emits LDS/STS (pointers kept
+// in the solver object lose their provenance and degrade to generic LD/ST - profiles/r1f).
+template <bool SG>
 struct WarpWs {
-  double* stage;  // [(N+1)][kStride]
-  double* P;      // [9][9]
-  double* T;      // [9][12]
-  double* G;      // [12][12]
-  double* pv;     // [3][9]
-  double* tv;     // [3][9]
-  double* gv;     // [3][12]
-  double* misc;   // [kMisc]
-  // stage_base == nullptr: the stage storage lives in front of the scratch area at `base`
-  MPCR_HD void bind(double* base, double* stage_base, int N) {
-    if (stage_base) {
-      stage = stage_base;
-      P = base;
-    } else {
-      stage = base;
-      P = base + (N + 1) * kStride;
-    }
-    T = P + 81;
-    G = T + 108;
-    pv = G + 144;
-    tv = pv + 27;
-    gv = tv + 27;
-    misc = gv + 36;
+  double* base_;   // host build (emulation): start of the workspace; unused on the device
+  double* stage_;  // SG only: global slab
+  int soff_;       // offset of the scratch area inside the shared/host workspace
+  MPCR_D double* sm() const {
+#if defined(__CUDA_ARCH__)
+    extern __shared__ double mpcr_dyn_smem[];
+    return mpcr_dyn_smem;
+#else
+    return base_;
+#endif
   }
-  MPCR_HD double* st(int k) const { return stage + k * kStride; }
+  MPCR_HD void bind(double* base, double* stage_base, int N) {
+    base_ = base;
+    stage_ = stage_base;
+    soff_ = SG ? 0 : (N + 1) * kStride;
+  }
+  MPCR_D double* P() const { return sm() + soff_; }            // [9][9]
+  MPCR_D double* T() const { return sm() + soff_ + 81; }       // [9][12]
+  MPCR_D double* G() const { return sm() + soff_ + 189; }      // [12][12]
+  MPCR_D double* pv() const { return sm() + soff_ + 333; }     // [3][9]
+  MPCR_D double* tv() const { return sm() + soff_ + 360; }     // [3][9]
+  MPCR_D double* gv() const { return sm() + soff_ + 387; }     // [3][12]
+  MPCR_D double* misc() const { return sm() + soff_ + 423; }   // [kMisc]
+  MPCR_D double* st(int k) const { return (SG ? stage_ : sm()) + k * kStride; }   // [(N+1)][kStride]
 };
 
 // packed slot of the sparse stage Hessian for entry (row, col) of the 12x12
@@ -212,13 +216,13 @@ struct RowState {
   double dsr[kNumRows];     // slack step of the current direction
 };
 
-template <int MODEL>
+template <int MODEL, bool SG = false>
 struct WarpSolver {
   const Config& cfg;
   const Params& p;        // per-problem copy (GA sweeps override the runtime parameters)
   const IpmOptions& o;
   const ProblemView& pb;
-  WarpWs ws;
+  WarpWs<SG> ws;
   int lane, N;
   bool act;
   // primal iterate
@@ -256,8 +260,8 @@ struct WarpSolver {
   MPCR_D bool on(int r) const { return (rowmask >> r) & 1u; }
   MPCR_D int prev_lane() const { return lane == 0 ? N - 1 : lane - 1; }
   MPCR_D int next_lane() const { return lane >= N - 1 ? 0 : lane + 1; }
-  MPCR_D double lo(int r) const { return ws.misc[r]; }
-  MPCR_D double hi(int r) const { return ws.misc[kNumRows + r]; }
+  MPCR_D double lo(int r) const { return ws.misc()[r]; }
+  MPCR_D double hi(int r) const { return ws.misc()[kNumRows + r]; }
 
   // original (unrelaxed, unscaled-row) bounds of row r
   MPCR_D void row_bounds(int r, double& l, double& h) const {
@@ -616,9 +620,9 @@ struct WarpSolver {
 
   MPCR_D bool riccati(double dw) {
     const double Ts = cfg.Ts;
-    double* P = ws.P;
-    double* T = ws.T;
-    double* G = ws.G;
+    double* P = ws.P();
+    double* T = ws.T();
+    double* G = ws.G();
     const int nrhs = cfg.wrap ? kRhs : 1;
     {
       const double* stN = ws.st(N);
@@ -631,7 +635,7 @@ struct WarpSolver {
       }
       if (lane < 27) {
         int j = lane / 9, a = lane % 9;
-        ws.pv[lane] = (j == 0) ? stN[kOffGs + a] : 0.0;
+        ws.pv()[lane] = (j == 0) ? stN[kOffGs + a] : 0.0;
       }
     }
     syncwarp();
@@ -647,11 +651,11 @@ struct WarpSolver {
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(pr, A, Ts, out);
         for (int c = 0; c < 12; ++c) T[lane * 12 + c] = out[c];
-        double t0 = ws.pv[lane];
+        double t0 = ws.pv()[lane];
         for (int c = 0; c < 6; ++c) t0 += pr[c] * st[kOffB + c];
-        ws.tv[lane] = t0;
-        ws.tv[9 + lane] = ws.pv[9 + lane];
-        ws.tv[18 + lane] = ws.pv[18 + lane];
+        ws.tv()[lane] = t0;
+        ws.tv()[9 + lane] = ws.pv()[9 + lane];
+        ws.tv()[18 + lane] = ws.pv()[18 + lane];
       }
       syncwarp();
       // ---- round 2: G[:, c] = M' T[:, c] + stage Hessian column ; g_j = grad_j + M' t_j
@@ -659,7 +663,7 @@ struct WarpSolver {
         const bool isvec = lane >= 12;
         const int j = lane - 12;
         double tc[9], A[21], out[12];
-        for (int r = 0; r < 9; ++r) tc[r] = isvec ? ws.tv[j * 9 + r] : T[r * 12 + lane];
+        for (int r = 0; r < 9; ++r) tc[r] = isvec ? ws.tv()[j * 9 + r] : T[r * 12 + lane];
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(tc, A, Ts, out);
         if (!isvec) {
@@ -669,11 +673,11 @@ struct WarpSolver {
           for (int r = 0; r < 12; ++r) {
             double g = out[r];
             if (j == 0) g += st[kOffGs + r];
-            ws.gv[j * 12 + r] = g;
+            ws.gv()[j * 12 + r] = g;
           }
           if (j >= 1) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
             double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
-            ws.gv[j * 12 + 9 + (j - 1)] += a;
+            ws.gv()[j * 12 + 9 + (j - 1)] += a;
           }
         }
       }
@@ -696,7 +700,7 @@ struct WarpSolver {
         const bool isvec = lane >= 12;
         const int c = lane;
         const int j = lane - 12;
-        const double* src = isvec ? (ws.gv + j * 12) : (G + c);
+        const double* src = isvec ? (ws.gv() + j * 12) : (G + c);
         const int sstride = isvec ? 1 : 12;
         const double r0 = src[9 * sstride], r1 = src[10 * sstride], r2 = src[11 * sstride];
         const double f0 = r0, f1 = r1 - l10 * f0, f2 = r2 - l20 * f0 - l21 * f1;
@@ -709,7 +713,7 @@ struct WarpSolver {
         kdst[0] = k0;
         kdst[kstride] = k1;
         kdst[2 * kstride] = k2;
-        double* pdst = isvec ? (ws.pv + j * 9) : (P + c);
+        double* pdst = isvec ? (ws.pv() + j * 9) : (P + c);
         const int pstride = isvec ? 1 : 9;
         for (int a = 0; a < 9; ++a)
           pdst[a * pstride] = src[a * sstride] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
@@ -805,7 +809,7 @@ struct WarpSolver {
       double t = shfl(dsh, prev_lane());
       dzp[6] = (lane == 0) ? 0.0 : t;
     }
-    double* loc = ws.T;   // scratch [(N+1)][7]: T (108) + G (144) are contiguous
+    double* loc = ws.T();   // scratch [(N+1)][7]: T (108) + G (144) are contiguous
     if (act) {
       const double* st = ws.st(lane);
       const double v12[12] = {dzp[0], dzp[1], dzp[2], dzp[3], dzp[4], dzp[5], dzp[6], 0, 0,
@@ -1080,7 +1084,7 @@ struct WarpSolver {
       n_bounds = (int)(warp_sum((double)nb) + 0.5);
     }
     // provisional (unscaled, unrelaxed) bounds so that lo()/hi() are defined early
-    if (lane < kNumRows) { ws.misc[lane] = -inf; ws.misc[kNumRows + lane] = inf; }
+    if (lane < kNumRows) { ws.misc()[lane] = -inf; ws.misc()[kNumRows + lane] = inf; }
     syncwarp();
 
     // ---- phase-loop state ------------------------------------------------------------
@@ -1147,8 +1151,8 @@ struct WarpSolver {
             else l = -inf;
             if (row_hasU(lane)) h += fmin(o.constr_viol_tol, o.bound_relax_factor * fmax(1.0, fabs(h)));
             else h = inf;
-            ws.misc[lane] = l;
-            ws.misc[kNumRows + lane] = h;
+            ws.misc()[lane] = l;
+            ws.misc()[kNumRows + lane] = h;
           }
           syncwarp();
         } else {
@@ -1527,7 +1531,7 @@ MPCR_HD int lam_g_stride(const Config& c) {
   return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
 }
 
-template <int MODEL>
+template <int MODEL, bool SG = false>
 MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                           int trace_rows, double* wsbase, double* stagebase) {
   const int N = cfg.N;
@@ -1569,7 +1573,7 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     syncwarp();
   }
   RowState rows;
-  WarpSolver<MODEL> solver(cfg, prm, pv, rows, wsbase, stagebase);
+  WarpSolver<MODEL, SG> solver(cfg, prm, pv, rows, wsbase, stagebase);
   solver.solve(so);
 }
 
