@@ -243,7 +243,10 @@ struct WarpSolver {
   // filter: one entry per lane
   double filt_th, filt_ph;
   int filt_n;
-  int colslot[12];          // packed slot of stage-Hessian entry (r, lane) for lanes 0..11
+  // packed slots of the stage-Hessian entries (r, lane), r = 0..11, one byte each (registers,
+  // no runtime-indexed local array): rows 0-7 in colslot_lo, rows 8-11 in colslot_hi
+  unsigned long long colslot_lo;
+  unsigned colslot_hi;
   double dwflag;            // 1 if diagonal entry (lane, lane) receives delta_w
 
   MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, RowState& rows,
@@ -253,7 +256,13 @@ struct WarpSolver {
     N = c.N;
     act = lane < N;
     ws.bind(wsbase, stagebase, N);
-    for (int r = 0; r < 12; ++r) colslot[r] = (lane < 12) ? (slot_of(r, lane) & 0xff) : kZeroSlot;
+    colslot_lo = 0ull;
+    colslot_hi = 0u;
+    for (int r = 0; r < 12; ++r) {
+      const unsigned long long v = (lane < 12) ? (unsigned long long)(slot_of(r, lane) & 0xff) : kZeroSlot;
+      if (r < 8) colslot_lo |= v << (8 * r);
+      else colslot_hi |= (unsigned)v << (8 * (r - 8));
+    }
     dwflag = (lane <= 6 || lane == 9 || lane == 10) ? 1.0 : 0.0;
   }
 
@@ -667,9 +676,14 @@ struct WarpSolver {
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(tc, A, Ts, out);
         if (!isvec) {
-          for (int r = 0; r < 12; ++r) G[r * 12 + lane] = out[r] + st[kOffHs + colslot[r]];
+#pragma unroll
+          for (int r = 0; r < 12; ++r) {
+            const int slot = (r < 8) ? (int)((colslot_lo >> (8 * r)) & 0xff) : (int)((colslot_hi >> (8 * (r - 8))) & 0xff);
+            G[r * 12 + lane] = out[r] + st[kOffHs + slot];
+          }
           G[lane * 12 + lane] += dwc;
         } else {
+#pragma unroll
           for (int r = 0; r < 12; ++r) {
             double g = out[r];
             if (j == 0) g += st[kOffGs + r];
@@ -715,6 +729,7 @@ struct WarpSolver {
         kdst[2 * kstride] = k2;
         double* pdst = isvec ? (ws.pv() + j * 9) : (P + c);
         const int pstride = isvec ? 1 : 9;
+#pragma unroll
         for (int a = 0; a < 9; ++a)
           pdst[a * pstride] = src[a * sstride] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
                               G[11 * 12 + a] * k2;
