@@ -95,6 +95,34 @@ def cpu_pool_rate(batch, n_problems, cores):
     return conv / dt, conv, dt
 
 
+def _cxx_chunk(args):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu_util import emu_solve
+    x0, up, s0, cx, cy = args
+    r = emu_solve(x0, up, s0, cx, cy, N=N_HORIZON, Ts=TS, lanes=True)
+    return int((r["status"] >= 0).sum())
+
+
+def cpu_cxx_rate(batch, n_problems, cores):
+    """Context only: the lane-solver SOURCE (mpcr_ipm_lanes.cuh: same IPM + Riccati as the kernels)
+    compiled for the host by tests/emu with g++ -O2, one process per core.  Not the oracle and not
+    the reference - an optimised C++ CPU port of the same algorithm."""
+    from multiprocessing import get_context
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu_util
+    emu_util.build_emu()                 # once, in the parent (the workers only load it)
+    per = max(1, n_problems // cores)
+    jobs = [tuple(batch[k][i * per:(i + 1) * per] for k in ("x0", "u_prev", "s0", "cx", "cy"))
+            for i in range(cores)]
+    ctx = get_context("fork")
+    with ctx.Pool(cores, initializer=_pool_init) as pool:
+        pool.map(_cxx_chunk, [tuple(a[:1] for a in j) for j in jobs])      # build + warm
+        t0 = time.perf_counter()
+        conv = sum(pool.map(_cxx_chunk, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+    return conv / dt, conv, dt
+
+
 # ---------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +295,16 @@ def run_gpu(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {nprob} problems of rank 0's batch, oracle/ipm.py (numpy port of "
                              f"the reference's IPOPT path), {cores} processes, {dt:.1f} s"}
+        cxx = None
+        if not args.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                rate, conv, dt = cpu_cxx_rate(host, min(B, 512 * cores), cores)
+                cxx = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port-cxx",
+                       "sample": f"first {min(B, 512 * cores)} problems, lane-solver source compiled for the host "
+                                 f"(g++ -O2, tests/emu), {cores} processes, {dt:.1f} s; context only"}
+            except Exception as exc:      # the C++ host build is test infrastructure: optional here
+                cxx = {"unavailable": repr(exc)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / max(1, args.steps),
@@ -290,6 +328,7 @@ def run_gpu(args):
                                  "algorithmic_bytes_per_launch": bytes_alg}},
             "cpu_baseline": cpu,
             "single_solve_latency": lat,
+            "cpu_baseline_cxx": cxx,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
