@@ -131,7 +131,10 @@ class ClosedLoopRollouts:
                 hist.append(dict(x=x.cpu().numpy().copy(), progress=progress.cpu().numpy().copy(),
                                  u0=u0.cpu().numpy().copy(), cx=cx.cpu().numpy().copy(),
                                  cy=cy.cpu().numpy().copy(), status=res.status.cpu().numpy().copy(),
-                                 U=res.U.cpu().numpy().copy()))
+                                 U=res.U.cpu().numpy().copy(), X=res.X.cpu().numpy().copy(),
+                                 S=res.S.cpu().numpy().copy(), eC=res.eC.cpu().numpy().copy(),
+                                 eL=res.eL.cpu().numpy().copy(), dist=dist.cpu().numpy().copy(),
+                                 sign=sign.cpu().numpy().copy()))
             x = t.where(done[:, None], x, x_new)
             x_new = t.empty_like(x)
             u_prev = u0

@@ -66,6 +66,15 @@ def test_closed_loop_steps_match_cpu_loop(t4):
             x = plant.blended_step(x, u0, 0.05)
             u_prev = u0
             u_warm = ref["U"]
+    # the recorded history writes out as a reference-format run (reference: Logger.py)
+    import pandas as pd
+    import tempfile
+    from mpc_racing_b200.Logger import write_rollout, member_names
+    with tempfile.TemporaryDirectory() as tmp:
+        d = write_rollout(hist, vehicle=0, runs_fp=tmp, Ts=0.05, name="gpu_run")
+        df = pd.read_csv(d + "/steps.csv")
+        assert list(df.columns) == member_names and len(df) == K
+        np.testing.assert_allclose(df["progress"], [h["progress"][0] for h in hist])
     ro.close()
 
 
