@@ -47,6 +47,10 @@ extern "C" {
 #define MPCR_KERNEL_WARP 1
 #define MPCR_KERNEL_LANES 2
 
+/* integrators of the NLP's dynamics rows (also used by mpcr_model_eval) */
+#define MPCR_INTEGRATOR_EULER 0
+#define MPCR_INTEGRATOR_RK4 1
+
 /* per-problem status codes */
 #define MPCR_SOLVE_SUCCEEDED 0
 #define MPCR_SOLVED_TO_ACCEPTABLE_LEVEL 1
@@ -85,7 +89,8 @@ typedef struct mpcr_config {
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
   double mu_init;
   int32_t solve_kernel;      /* MPCR_KERNEL_* (0 = auto) */
-  int32_t reserved_;
+  int32_t integrator;        /* MPCR_INTEGRATOR_EULER (reference, default) or MPCR_INTEGRATOR_RK4 (extension;
+                              * solved by the lane kernel) */
 } mpcr_config;
 
 typedef struct mpcr_handle mpcr_handle;
@@ -175,8 +180,6 @@ int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x, const dou
  * hess[B,8,8] = sum_k lam[b,k] d2 x+_k/d(x,u)^2 (or NULL; needs lam[B,6]).
  * integrator: MPCR_INTEGRATOR_EULER = the explicit-Euler maps the reference's NLP uses,
  * MPCR_INTEGRATOR_RK4 = classical RK4 of the same vector field (extension, north-star item 2). */
-#define MPCR_INTEGRATOR_EULER 0
-#define MPCR_INTEGRATOR_RK4 1
 int mpcr_model_eval(mpcr_handle* h, int model, int integrator, int B, const double* x, const double* u,
                     double Ts, const double* lam, double* f, double* jac, double* hess,
                     void* cuda_stream);

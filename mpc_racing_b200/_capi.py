@@ -30,7 +30,7 @@ class MpcrConfig(C.Structure):
         ("tol", C.c_double), ("acceptable_tol", C.c_double),
         ("dual_inf_tol", C.c_double), ("constr_viol_tol", C.c_double),
         ("compl_inf_tol", C.c_double), ("mu_init", C.c_double),
-        ("solve_kernel", C.c_int32), ("reserved_", C.c_int32),
+        ("solve_kernel", C.c_int32), ("integrator", C.c_int32),
     ]
 
 

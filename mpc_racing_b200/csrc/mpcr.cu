@@ -60,7 +60,7 @@ static SolveKernelFn pick_kernel(int model, bool stage_global) {
 
 // Throughput kernel: one problem per LANE (mpcr_ipm_lanes.cuh).  Block = one warp; warp w owns
 // the workspace slab [w * ws_doubles * 32, ...) laid out [element][lane] (coalesced).
-template <int MODEL>
+template <int MODEL, int IG>
 __global__ void __launch_bounds__(32, 1)
 lane_solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
                   int trace_rows, double* __restrict__ ws, int ws_doubles) {
@@ -68,15 +68,20 @@ lane_solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const Ba
   const int b = blockIdx.x * 32 + lane;
   if (b >= B) return;
   double* w = ws + (size_t)blockIdx.x * ws_doubles * 32 + lane;
-  lane_solve_problem<MODEL>(cfg, in, out, b, trace_rows, w);
+  lane_solve_problem<MODEL, IG>(cfg, in, out, b, trace_rows, w);
 }
 
 typedef void (*LaneKernelFn)(const Config, const BatchIn, const BatchOut, int, int, double*, int);
 
-static LaneKernelFn pick_lane_kernel(int model) {
-  if (model == kDynamic) return lane_solve_kernel<kDynamic>;
-  if (model == kKinematic) return lane_solve_kernel<kKinematic>;
-  return lane_solve_kernel<kBlended>;
+static LaneKernelFn pick_lane_kernel(int model, int integrator) {
+  if (integrator == MPCR_INTEGRATOR_RK4) {
+    if (model == kDynamic) return lane_solve_kernel<kDynamic, 1>;
+    if (model == kKinematic) return lane_solve_kernel<kKinematic, 1>;
+    return lane_solve_kernel<kBlended, 1>;
+  }
+  if (model == kDynamic) return lane_solve_kernel<kDynamic, 0>;
+  if (model == kKinematic) return lane_solve_kernel<kKinematic, 0>;
+  return lane_solve_kernel<kBlended, 0>;
 }
 
 // DFMA-chain microbenchmark: the measured fp64 roofline denominator
@@ -164,7 +169,7 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
     h->stage_global = e ? (atoi(e) != 0) : false;
   }
   h->kernel = pick_kernel(h->cfg.model, h->stage_global);
-  h->lane_kernel = pick_lane_kernel(h->cfg.model);
+  h->lane_kernel = pick_lane_kernel(h->cfg.model, h->cfg.integrator);
   h->kernel_sel = cfg->solve_kernel;
   {
     const char* e = getenv("MPCR_KERNEL");
@@ -239,7 +244,7 @@ extern "C" int mpcr_last_kernel_ms(mpcr_handle* h, float* ms) {
 
 static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut& out,
                         int trace_rows, cudaStream_t st) {
-  const bool lanes = h->kernel_sel == MPCR_KERNEL_LANES ||
+  const bool lanes = h->kernel_sel == MPCR_KERNEL_LANES || h->cfg.integrator == MPCR_INTEGRATOR_RK4 ||
                      (h->kernel_sel == MPCR_KERNEL_AUTO && B >= h->lanes_min_batch);
   if (lanes) {
     const size_t warps = ((size_t)B + 31) / 32;

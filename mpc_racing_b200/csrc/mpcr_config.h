@@ -41,7 +41,7 @@ inline void config_default(mpcr_config* c) {
   c->compl_inf_tol = 1e-4;
   c->mu_init = 0.1;
   c->solve_kernel = MPCR_KERNEL_AUTO;
-  c->reserved_ = 0;
+  c->integrator = MPCR_INTEGRATOR_EULER;
 }
 
 inline void config_convert(const mpcr_config& c, Config* out) {
@@ -51,6 +51,7 @@ inline void config_convert(const mpcr_config& c, Config* out) {
   k.model = c.model;
   k.wrap = c.wrap_constraint;
   k.lane_con = c.lane_constraint;
+  k.integrator = c.integrator;
   Params& p = k.p;
   p.lambda_s = c.lambda_s;
   p.alpha_L = c.alpha_L;
@@ -123,6 +124,11 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.max_iter < 0) { *why = "max_iter must be >= 0"; return false; }
   if (c.n_exp < 1.0) { *why = "n_exp must be >= 1"; return false; }
   if (c.solve_kernel < 0 || c.solve_kernel > 2) { *why = "unknown solve_kernel"; return false; }
+  if (c.integrator < 0 || c.integrator > 1) { *why = "unknown integrator"; return false; }
+  if (c.integrator == MPCR_INTEGRATOR_RK4 && c.solve_kernel == MPCR_KERNEL_WARP) {
+    *why = "the RK4 integrator is implemented by the lane kernel only";
+    return false;
+  }
   return true;
 }
 

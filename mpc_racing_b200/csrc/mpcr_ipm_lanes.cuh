@@ -25,6 +25,7 @@
 // on the CPU as test infrastructure - the product path is the CUDA build.
 #pragma once
 #include "mpcr_ipm.cuh"
+#include "mpcr_rk4.cuh"
 
 namespace mpcr {
 
@@ -56,8 +57,8 @@ constexpr int RRD = RVU + kNumRows;
 constexpr int RDSR = RRD + kNumRows;
 constexpr int RTRD = RDSR + kNumRows;
 constexpr int RDYD = RTRD + kNumRows;   // dual step of the row multiplier (current direction)
-constexpr int A = RDYD + kNumRows;      // StageLin (21)
-constexpr int HSD = A + 21;             // derivative part of the stage Hessian: (X,Y,s) block (6) + model block (21)
+constexpr int A = RDYD + kNumRows;      // stage linearisation: 21 (Euler) / 32 (RK4, see lane_lin_rk4)
+constexpr int HSD = A + 32;             // derivative part of the stage Hessian: (X,Y,s) block (6) + model block (21)
 constexpr int GC = HSD + 27;            // df * grad cost of state k+1 over (X, Y, s, vx, vy) (5)
 constexpr int GCZ = GC + 5;             // ddl * grad e_C of state k+1 over (X, Y, s) (3)
 constexpr int SIGC = GCZ + 3;           // steer_k - steer_{k-1} (0 for k = 0)
@@ -96,43 +97,116 @@ MPCR_HD constexpr int p9(int i, int j) {
   return (i <= j) ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
 }
 
-// t[k] = sum_j P[k][j] M[j][c]  (column c of M = [A B], see mulM), P packed symmetric
-template <int C>
+// Stage linearisation as the lane solver stores it: entries 0..20 are StageLin (aX[3], aY[3],
+// d[3][3], bu[3][2]); with the RK4 integrator the map's Jacobian has 11 more non-trivial entries:
+//   21..23  dX+/d(r, thr, st)      24..26  dY+/d(r, thr, st)
+//   27..30  dyaw+/d(v_x, v_y, thr, st)      31  dyaw+/dr  (= Ts for Euler)
+constexpr int kLinEuler = 21, kLinRk4 = 32;
+template <int IG> MPCR_HD constexpr int lin_count() { return IG ? kLinRk4 : kLinEuler; }
+
+// out = M' v with M = [A B] (9 x 12), cf. mulM
+template <int IG>
+MPCR_D void mulMx(const double* v, const double* A, double Ts, double* out) {
+  if (!IG) { mulM(v, A, Ts, out); return; }
+  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15, *xe = A + 21, *ye = A + 24, *aw = A + 27;
+  const double tsr = A[31];
+  out[0] = v[0];
+  out[1] = v[1];
+  out[2] = aX[0] * v[0] + aY[0] * v[1] + v[2];
+  out[3] = aX[1] * v[0] + aY[1] * v[1] + aw[0] * v[2] + d[0] * v[3] + d[3] * v[4] + d[6] * v[5];
+  out[4] = aX[2] * v[0] + aY[2] * v[1] + aw[1] * v[2] + d[1] * v[3] + d[4] * v[4] + d[7] * v[5];
+  out[5] = xe[0] * v[0] + ye[0] * v[1] + tsr * v[2] + d[2] * v[3] + d[5] * v[4] + d[8] * v[5];
+  out[6] = v[6];
+  out[7] = 0.0;
+  out[8] = 0.0;
+  out[9] = xe[1] * v[0] + ye[1] * v[1] + aw[2] * v[2] + bu[0] * v[3] + bu[2] * v[4] + bu[4] * v[5] + v[7];
+  out[10] = xe[2] * v[0] + ye[2] * v[1] + aw[3] * v[2] + bu[1] * v[3] + bu[3] * v[4] + bu[5] * v[5] + v[8];
+  out[11] = v[6];
+}
+
+// zn = M [z; w], cf. applyM
+template <int IG>
+MPCR_D void applyMx(const double* z, const double* w, const double* A, double Ts, double* zn) {
+  applyM(z, w, A, Ts, zn);
+  if (IG) {
+    const double *xe = A + 21, *ye = A + 24, *aw = A + 27;
+    zn[0] += xe[0] * z[5] + xe[1] * w[0] + xe[2] * w[1];
+    zn[1] += ye[0] * z[5] + ye[1] * w[0] + ye[2] * w[1];
+    zn[2] = z[2] + aw[0] * z[3] + aw[1] * z[4] + A[31] * z[5] + aw[2] * w[0] + aw[3] * w[1];
+  }
+}
+
+// t[k] = sum_j P[k][j] M[j][c]  (column c of M = [A B]), P packed symmetric
+template <int C, int IG>
 MPCR_D void p_times_mcol(const double* P, const double* A, double Ts, double* t) {
-  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15;
+  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15, *xe = A + 21, *ye = A + 24, *aw = A + 27;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     double v;
     if (C == 0) v = P[p9(k, 0)];
     else if (C == 1) v = P[p9(k, 1)];
     else if (C == 2) v = aX[0] * P[p9(k, 0)] + aY[0] * P[p9(k, 1)] + P[p9(k, 2)];
-    else if (C == 3) v = aX[1] * P[p9(k, 0)] + aY[1] * P[p9(k, 1)] + d[0] * P[p9(k, 3)] + d[3] * P[p9(k, 4)] + d[6] * P[p9(k, 5)];
-    else if (C == 4) v = aX[2] * P[p9(k, 0)] + aY[2] * P[p9(k, 1)] + d[1] * P[p9(k, 3)] + d[4] * P[p9(k, 4)] + d[7] * P[p9(k, 5)];
-    else if (C == 5) v = Ts * P[p9(k, 2)] + d[2] * P[p9(k, 3)] + d[5] * P[p9(k, 4)] + d[8] * P[p9(k, 5)];
+    else if (C == 3) v = aX[1] * P[p9(k, 0)] + aY[1] * P[p9(k, 1)] + d[0] * P[p9(k, 3)] + d[3] * P[p9(k, 4)] + d[6] * P[p9(k, 5)] + (IG ? aw[0] * P[p9(k, 2)] : 0.0);
+    else if (C == 4) v = aX[2] * P[p9(k, 0)] + aY[2] * P[p9(k, 1)] + d[1] * P[p9(k, 3)] + d[4] * P[p9(k, 4)] + d[7] * P[p9(k, 5)] + (IG ? aw[1] * P[p9(k, 2)] : 0.0);
+    else if (C == 5) v = (IG ? A[31] : Ts) * P[p9(k, 2)] + d[2] * P[p9(k, 3)] + d[5] * P[p9(k, 4)] + d[8] * P[p9(k, 5)] + (IG ? xe[0] * P[p9(k, 0)] + ye[0] * P[p9(k, 1)] : 0.0);
     else if (C == 6) v = P[p9(k, 6)];
-    else if (C == 9) v = bu[0] * P[p9(k, 3)] + bu[2] * P[p9(k, 4)] + bu[4] * P[p9(k, 5)] + P[p9(k, 7)];
-    else if (C == 10) v = bu[1] * P[p9(k, 3)] + bu[3] * P[p9(k, 4)] + bu[5] * P[p9(k, 5)] + P[p9(k, 8)];
+    else if (C == 9) v = bu[0] * P[p9(k, 3)] + bu[2] * P[p9(k, 4)] + bu[4] * P[p9(k, 5)] + P[p9(k, 7)] + (IG ? xe[1] * P[p9(k, 0)] + ye[1] * P[p9(k, 1)] + aw[2] * P[p9(k, 2)] : 0.0);
+    else if (C == 10) v = bu[1] * P[p9(k, 3)] + bu[3] * P[p9(k, 4)] + bu[5] * P[p9(k, 5)] + P[p9(k, 8)] + (IG ? xe[2] * P[p9(k, 0)] + ye[2] * P[p9(k, 1)] + aw[3] * P[p9(k, 2)] : 0.0);
     else if (C == 11) v = P[p9(k, 6)];
     else v = 0.0;   // columns 7, 8 of M are zero
     t[k] = v;
   }
 }
 
-// entry r of M' t (row r of mulM's output), compile-time r
-template <int R>
+// entry r of M' t (row r of mulMx's output), compile-time r
+template <int R, int IG>
 MPCR_D double mt_entry(const double* v, const double* A, double Ts) {
-  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15;
+  const double *aX = A, *aY = A + 3, *d = A + 6, *bu = A + 15, *xe = A + 21, *ye = A + 24, *aw = A + 27;
   if (R == 0) return v[0];
   if (R == 1) return v[1];
   if (R == 2) return aX[0] * v[0] + aY[0] * v[1] + v[2];
-  if (R == 3) return aX[1] * v[0] + aY[1] * v[1] + d[0] * v[3] + d[3] * v[4] + d[6] * v[5];
-  if (R == 4) return aX[2] * v[0] + aY[2] * v[1] + d[1] * v[3] + d[4] * v[4] + d[7] * v[5];
-  if (R == 5) return Ts * v[2] + d[2] * v[3] + d[5] * v[4] + d[8] * v[5];
+  if (R == 3) return aX[1] * v[0] + aY[1] * v[1] + d[0] * v[3] + d[3] * v[4] + d[6] * v[5] + (IG ? aw[0] * v[2] : 0.0);
+  if (R == 4) return aX[2] * v[0] + aY[2] * v[1] + d[1] * v[3] + d[4] * v[4] + d[7] * v[5] + (IG ? aw[1] * v[2] : 0.0);
+  if (R == 5) return (IG ? A[31] : Ts) * v[2] + d[2] * v[3] + d[5] * v[4] + d[8] * v[5] + (IG ? xe[0] * v[0] + ye[0] * v[1] : 0.0);
   if (R == 6) return v[6];
-  if (R == 9) return bu[0] * v[3] + bu[2] * v[4] + bu[4] * v[5] + v[7];
-  if (R == 10) return bu[1] * v[3] + bu[3] * v[4] + bu[5] * v[5] + v[8];
+  if (R == 9) return bu[0] * v[3] + bu[2] * v[4] + bu[4] * v[5] + v[7] + (IG ? xe[1] * v[0] + ye[1] * v[1] + aw[2] * v[2] : 0.0);
+  if (R == 10) return bu[1] * v[3] + bu[3] * v[4] + bu[5] * v[5] + v[8] + (IG ? xe[2] * v[0] + ye[2] * v[1] + aw[3] * v[2] : 0.0);
   if (R == 11) return v[6];
   return 0.0;
+}
+
+// value + linearisation (+ lam-weighted Hessian) of one stage in the lane solver's layout
+template <int MODEL, int IG>
+MPCR_D void lane_lin(const double* x, const double* u, double Ts, const double* lam, double* A,
+                     double* hm) {
+  if (!IG) {
+    StageLin lin;
+    lin_model(MODEL, x, u, Ts, lam, nullptr, lin, hm);
+    for (int a = 0; a < 3; ++a) { A[a] = lin.aX[a]; A[3 + a] = lin.aY[a]; }
+    for (int i = 0; i < 3; ++i)
+      for (int a = 0; a < 3; ++a) A[6 + 3 * i + a] = lin.d[i][a];
+    for (int i = 0; i < 3; ++i)
+      for (int a = 0; a < 2; ++a) A[15 + 2 * i + a] = lin.bu[i][a];
+  } else {
+    double f[6], J[6][6];
+    rk4_model(MODEL, x, u, Ts, lam, f, J, hm);
+    for (int a = 0; a < 3; ++a) { A[a] = J[0][a]; A[3 + a] = J[1][a]; A[21 + a] = J[0][3 + a]; A[24 + a] = J[1][3 + a]; }
+    for (int i = 0; i < 3; ++i) {
+      for (int a = 0; a < 3; ++a) A[6 + 3 * i + a] = J[3 + i][1 + a];
+      for (int a = 0; a < 2; ++a) A[15 + 2 * i + a] = J[3 + i][4 + a];
+    }
+    A[27] = J[2][1];
+    A[28] = J[2][2];
+    A[29] = J[2][4];
+    A[30] = J[2][5];
+    A[31] = J[2][3];
+  }
+}
+
+template <int MODEL, int IG>
+MPCR_D void lane_step(const double* x, const double* u, double Ts, double* f) {
+  if (!IG) f_model(MODEL, x, u, Ts, f);
+  else rk4_model(MODEL, x, u, Ts, nullptr, f, nullptr, nullptr);
 }
 
 // dense value of the packed stage Hessian at (r, c) from a register copy hs[32]
@@ -143,8 +217,9 @@ MPCR_HD double hs_at(const double* hs, int r, int c) {
 MPCR_HD constexpr bool dw_diag(int r) { return r <= 6 || r == 9 || r == 10; }
 
 // ---------------------------------------------------------------------------
-template <int MODEL>
+template <int MODEL, int IG = 0>
 struct LaneSolver {
+  static constexpr int NA = IG ? kLinRk4 : kLinEuler;
   const Config& cfg;
   const Params& p;
   const IpmOptions& o;
@@ -246,7 +321,7 @@ struct LaneSolver {
         uk[1] = pb.u_warm[N + src];
       }
       double fn[6];
-      f_dynamic(xr, uk, cfg.Ts, fn);                     // always f_vehicle (MPC.py:129)
+      lane_step<kDynamic, IG>(xr, uk, cfg.Ts, fn);       // always f_vehicle (MPC.py:129)
       for (int a = 0; a < 6; ++a) {
         xr[a] = fn[a];
         w.s(k, lw::X + a) = fn[a];
@@ -323,9 +398,9 @@ struct LaneSolver {
       uk[0] = w.s(k, lw::U);
       uk[1] = w.s(k, lw::U + 1);
       for (int a = 0; a < 6; ++a) lamk[a] = (mode == 0) ? w.s(k, lw::LAM + a) : 0.0;
-      StageLin lin;
+      double A[kLinRk4];
       double hm[kHmDoubles];
-      lin_model(MODEL, xp, uk, Ts, lamk, nullptr, lin, hm);
+      lane_lin<MODEL, IG>(xp, uk, Ts, lamk, A, hm);
       StageCost sc;
       stage_cost(p, pb.cx, pb.cy, xk, shk, 2, sc);
       double gcost[5], gC[3];
@@ -351,13 +426,7 @@ struct LaneSolver {
         }
       }
       // ---- stage record ------------------------------------------------------------
-      double A[21];
-      for (int a = 0; a < 3; ++a) { A[a] = lin.aX[a]; A[3 + a] = lin.aY[a]; }
-      for (int i = 0; i < 3; ++i)
-        for (int a = 0; a < 3; ++a) A[6 + 3 * i + a] = lin.d[i][a];
-      for (int i = 0; i < 3; ++i)
-        for (int a = 0; a < 2; ++a) A[15 + 2 * i + a] = lin.bu[i][a];
-      for (int a = 0; a < 21; ++a) w.s(k, lw::A + a) = A[a];
+      for (int a = 0; a < NA; ++a) w.s(k, lw::A + a) = A[a];
       for (int a = 0; a < 6; ++a) w.s(k, lw::HSD + a) = hcp[a];
       for (int a = 0; a < kHmDoubles; ++a) {
         double v = (mode == 0) ? -hm[a] : 0.0;
@@ -383,13 +452,18 @@ struct LaneSolver {
         if (k >= 1) gmax = fmax(gmax, fabs(bd2 * (sig_prev_for_scale - sigc)));
         sig_prev_for_scale = sigc;
         double rm[6];
-        rm[0] = fmax(1.0, fmax(fabs(lin.aX[0]), fmax(fabs(lin.aX[1]), fabs(lin.aX[2]))));
-        rm[1] = fmax(1.0, fmax(fabs(lin.aY[0]), fmax(fabs(lin.aY[1]), fabs(lin.aY[2]))));
+        rm[0] = fmax(1.0, fmax(fabs(A[0]), fmax(fabs(A[1]), fabs(A[2]))));
+        rm[1] = fmax(1.0, fmax(fabs(A[3]), fmax(fabs(A[4]), fabs(A[5]))));
         rm[2] = fmax(1.0, fabs(Ts));
+        if (IG) {
+          for (int a = 0; a < 3; ++a) { rm[0] = fmax(rm[0], fabs(A[21 + a])); rm[1] = fmax(rm[1], fabs(A[24 + a])); }
+          rm[2] = fmax(1.0, fabs(A[31]));
+          for (int a = 0; a < 4; ++a) rm[2] = fmax(rm[2], fabs(A[27 + a]));
+        }
         for (int i = 0; i < 3; ++i) {
           double mm = 1.0;
-          for (int a = 0; a < 3; ++a) mm = fmax(mm, fabs(lin.d[i][a]));
-          for (int a = 0; a < 2; ++a) mm = fmax(mm, fabs(lin.bu[i][a]));
+          for (int a = 0; a < 3; ++a) mm = fmax(mm, fabs(A[6 + 3 * i + a]));
+          for (int a = 0; a < 2; ++a) mm = fmax(mm, fabs(A[15 + 2 * i + a]));
           rm[3 + i] = mm;
         }
         for (int a = 0; a < 6; ++a)
@@ -405,7 +479,7 @@ struct LaneSolver {
         double lv[9], out[12];
         for (int a = 0; a < 6; ++a) lv[a] = lamk[a];
         lv[6] = lv[7] = lv[8] = 0.0;
-        mulM(lv, A, Ts, out);
+        mulMx<IG>(lv, A, Ts, out);
         const double yprog = w.s(k, lw::RYD + kProg);
         const double ydthr = on(m, kDThr) ? w.s(k, lw::RYD + kDThr) : 0.0;
         const double ydst = on(m, kDSt) ? w.s(k, lw::RYD + kDSt) : 0.0;
@@ -617,7 +691,7 @@ struct LaneSolver {
       const double bq = (mode == 0) ? bsig : 0.0;
       const double dthr = wrap0 ? 0.0 : q.Dthr;
       const double dst = wrap0 ? 0.0 : q.Dst;
-      double hs[32], gs[12], A[21], b[6];
+      double hs[32], gs[12], A[kLinRk4], b[6];
       for (int a = 0; a < 6; ++a) hs[a] = w.s(k, lw::HSD + a);
       for (int a = 0; a < 21; ++a) hs[6 + a] = w.s(k, lw::HSD + 6 + a);
       hs[0] += Dlane_p * gCp[0] * gCp[0];
@@ -654,28 +728,28 @@ struct LaneSolver {
       gs[11] = q.eprog;
       for (int a = 0; a < 32; ++a) w.s(k, lw::HS + a) = hs[a];
       for (int a = 0; a < 12; ++a) w.s(k, lw::GS + a) = gs[a];
-      for (int a = 0; a < 21; ++a) A[a] = w.s(k, lw::A + a);
+      for (int a = 0; a < NA; ++a) A[a] = w.s(k, lw::A + a);
       for (int a = 0; a < 6; ++a)
         b[a] = (csel == 0) ? 0.0 : -w.s(k, (csel == 1 ? lw::CRES : lw::CSOC) + a);
       // ---- G columns of the inputs w = (thr, st, ds): Gw[i][r] = G[r][9 + i] ----------------
       double Gw[3][12];
       {
         double t[9];
-        p_times_mcol<9>(P, A, Ts, t);
-        Gw[0][0] = mt_entry<0>(t, A, Ts); Gw[0][1] = mt_entry<1>(t, A, Ts); Gw[0][2] = mt_entry<2>(t, A, Ts);
-        Gw[0][3] = mt_entry<3>(t, A, Ts); Gw[0][4] = mt_entry<4>(t, A, Ts); Gw[0][5] = mt_entry<5>(t, A, Ts);
-        Gw[0][6] = mt_entry<6>(t, A, Ts); Gw[0][7] = 0.0; Gw[0][8] = 0.0;
-        Gw[0][9] = mt_entry<9>(t, A, Ts); Gw[0][10] = mt_entry<10>(t, A, Ts); Gw[0][11] = mt_entry<11>(t, A, Ts);
-        p_times_mcol<10>(P, A, Ts, t);
-        Gw[1][0] = mt_entry<0>(t, A, Ts); Gw[1][1] = mt_entry<1>(t, A, Ts); Gw[1][2] = mt_entry<2>(t, A, Ts);
-        Gw[1][3] = mt_entry<3>(t, A, Ts); Gw[1][4] = mt_entry<4>(t, A, Ts); Gw[1][5] = mt_entry<5>(t, A, Ts);
-        Gw[1][6] = mt_entry<6>(t, A, Ts); Gw[1][7] = 0.0; Gw[1][8] = 0.0;
-        Gw[1][9] = Gw[0][10]; Gw[1][10] = mt_entry<10>(t, A, Ts); Gw[1][11] = mt_entry<11>(t, A, Ts);
-        p_times_mcol<11>(P, A, Ts, t);
-        Gw[2][0] = mt_entry<0>(t, A, Ts); Gw[2][1] = mt_entry<1>(t, A, Ts); Gw[2][2] = mt_entry<2>(t, A, Ts);
-        Gw[2][3] = mt_entry<3>(t, A, Ts); Gw[2][4] = mt_entry<4>(t, A, Ts); Gw[2][5] = mt_entry<5>(t, A, Ts);
-        Gw[2][6] = mt_entry<6>(t, A, Ts); Gw[2][7] = 0.0; Gw[2][8] = 0.0;
-        Gw[2][9] = Gw[0][11]; Gw[2][10] = Gw[1][11]; Gw[2][11] = mt_entry<11>(t, A, Ts);
+        p_times_mcol<9, IG>(P, A, Ts, t);
+        Gw[0][0] = mt_entry<0, IG>(t, A, Ts); Gw[0][1] = mt_entry<1, IG>(t, A, Ts); Gw[0][2] = mt_entry<2, IG>(t, A, Ts);
+        Gw[0][3] = mt_entry<3, IG>(t, A, Ts); Gw[0][4] = mt_entry<4, IG>(t, A, Ts); Gw[0][5] = mt_entry<5, IG>(t, A, Ts);
+        Gw[0][6] = mt_entry<6, IG>(t, A, Ts); Gw[0][7] = 0.0; Gw[0][8] = 0.0;
+        Gw[0][9] = mt_entry<9, IG>(t, A, Ts); Gw[0][10] = mt_entry<10, IG>(t, A, Ts); Gw[0][11] = mt_entry<11, IG>(t, A, Ts);
+        p_times_mcol<10, IG>(P, A, Ts, t);
+        Gw[1][0] = mt_entry<0, IG>(t, A, Ts); Gw[1][1] = mt_entry<1, IG>(t, A, Ts); Gw[1][2] = mt_entry<2, IG>(t, A, Ts);
+        Gw[1][3] = mt_entry<3, IG>(t, A, Ts); Gw[1][4] = mt_entry<4, IG>(t, A, Ts); Gw[1][5] = mt_entry<5, IG>(t, A, Ts);
+        Gw[1][6] = mt_entry<6, IG>(t, A, Ts); Gw[1][7] = 0.0; Gw[1][8] = 0.0;
+        Gw[1][9] = Gw[0][10]; Gw[1][10] = mt_entry<10, IG>(t, A, Ts); Gw[1][11] = mt_entry<11, IG>(t, A, Ts);
+        p_times_mcol<11, IG>(P, A, Ts, t);
+        Gw[2][0] = mt_entry<0, IG>(t, A, Ts); Gw[2][1] = mt_entry<1, IG>(t, A, Ts); Gw[2][2] = mt_entry<2, IG>(t, A, Ts);
+        Gw[2][3] = mt_entry<3, IG>(t, A, Ts); Gw[2][4] = mt_entry<4, IG>(t, A, Ts); Gw[2][5] = mt_entry<5, IG>(t, A, Ts);
+        Gw[2][6] = mt_entry<6, IG>(t, A, Ts); Gw[2][7] = 0.0; Gw[2][8] = 0.0;
+        Gw[2][9] = Gw[0][11]; Gw[2][10] = Gw[1][11]; Gw[2][11] = mt_entry<11, IG>(t, A, Ts);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -712,7 +786,7 @@ struct LaneSolver {
             tv[r] = t0;
           }
           double g[12];
-          mulM(tv, A, Ts, g);
+          mulMx<IG>(tv, A, Ts, g);
           if (j == 0) {
 #pragma unroll
             for (int r = 0; r < 12; ++r) g[r] += gs[r];
@@ -772,15 +846,15 @@ struct LaneSolver {
     w.s(k, lw::K + 1 * 9 + C) = k1;
     w.s(k, lw::K + 2 * 9 + C) = k2;
     double t[9];
-    p_times_mcol<C>(P, A, Ts, t);
+    p_times_mcol<C, IG>(P, A, Ts, t);
     double g[9];
-    g[0] = mt_entry<0>(t, A, Ts);
-    if (C >= 1) g[1] = mt_entry<1>(t, A, Ts);
-    if (C >= 2) g[2] = mt_entry<2>(t, A, Ts);
-    if (C >= 3) g[3] = mt_entry<3>(t, A, Ts);
-    if (C >= 4) g[4] = mt_entry<4>(t, A, Ts);
-    if (C >= 5) g[5] = mt_entry<5>(t, A, Ts);
-    if (C >= 6) g[6] = mt_entry<6>(t, A, Ts);
+    g[0] = mt_entry<0, IG>(t, A, Ts);
+    if (C >= 1) g[1] = mt_entry<1, IG>(t, A, Ts);
+    if (C >= 2) g[2] = mt_entry<2, IG>(t, A, Ts);
+    if (C >= 3) g[3] = mt_entry<3, IG>(t, A, Ts);
+    if (C >= 4) g[4] = mt_entry<4, IG>(t, A, Ts);
+    if (C >= 5) g[5] = mt_entry<5, IG>(t, A, Ts);
+    if (C >= 6) g[6] = mt_entry<6, IG>(t, A, Ts);
     if (C >= 7) g[7] = 0.0;
     if (C >= 8) g[8] = 0.0;
 #pragma unroll
@@ -803,8 +877,8 @@ struct LaneSolver {
       for (int a = 0; a < 9; ++a) z[j][a] = 0.0;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-      double A[21], Kk[27];
-      for (int a = 0; a < 21; ++a) A[a] = w.s(k, lw::A + a);
+      double A[kLinRk4], Kk[27];
+      for (int a = 0; a < NA; ++a) A[a] = w.s(k, lw::A + a);
       for (int a = 0; a < 27; ++a) Kk[a] = w.s(k, lw::K + a);
 #pragma unroll
       for (int j = 0; j < kRhs; ++j) {
@@ -818,7 +892,7 @@ struct LaneSolver {
             ww[i] = acc;
           }
           double zn[9];
-          applyM(z[j], ww, A, Ts, zn);
+          applyMx<IG>(z[j], ww, A, Ts, zn);
           if (j == 0 && csel != 0) {
 #pragma unroll
             for (int a = 0; a < 6; ++a) zn[a] -= w.s(k, (csel == 1 ? lw::CRES : lw::CSOC) + a);
@@ -896,20 +970,16 @@ struct LaneSolver {
       for (int a = 0; a < 9; ++a) w.s(k, lw::DX + a) = dcur[a];
       // ---- costate recursion: pi_k = loc_k + A_k' pi_{k+1} -----------------------------------
       {
-        double hs[32], A[21];
+        double hs[32], A[kLinRk4];
         for (int a = 0; a < 32; ++a) hs[a] = w.s(k, lw::HS + a);
-        for (int a = 0; a < 21; ++a) A[a] = w.s(k, lw::A + a);
+        for (int a = 0; a < NA; ++a) A[a] = w.s(k, lw::A + a);
         const double v12[12] = {dprev[0], dprev[1], dprev[2], dprev[3], dprev[4], dprev[5], dprev[6],
                                 0.0, 0.0, dcur[7], dcur[8], 0.0};
-        const double *aX = A, *aY = A + 3, *d = A + 6;
-        double qv[7];
-        qv[0] = pi[0];
-        qv[1] = pi[1];
-        qv[2] = aX[0] * pi[0] + aY[0] * pi[1] + pi[2];
-        qv[3] = aX[1] * pi[0] + aY[1] * pi[1] + d[0] * pi[3] + d[3] * pi[4] + d[6] * pi[5];
-        qv[4] = aX[2] * pi[0] + aY[2] * pi[1] + d[1] * pi[3] + d[4] * pi[4] + d[7] * pi[5];
-        qv[5] = Ts * pi[2] + d[2] * pi[3] + d[5] * pi[4] + d[8] * pi[5];
-        qv[6] = pi[6];
+        double qv[12];
+        {
+          const double pi9[9] = {pi[0], pi[1], pi[2], pi[3], pi[4], pi[5], pi[6], 0.0, 0.0};
+          mulMx<IG>(pi9, A, Ts, qv);       // A_k' pi_{k+1}; entries 0..6 are used
+        }
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
           double acc = w.s(k, lw::GS + a);
@@ -1008,7 +1078,7 @@ struct LaneSolver {
       tu[0] = w.s(k, lw::U) + at * w.s(k, lw::DX + 7);
       tu[1] = w.s(k, lw::U + 1) + at * w.s(k, lw::DX + 8);
       double f[6];
-      f_model(MODEL, xp, tu, Ts, f);
+      lane_step<MODEL, IG>(xp, tu, Ts, f);
       StageCost sc;
       stage_cost(p, pb.cx, pb.cy, tx, tsh, 0, sc);
       double fl = sc.val;
@@ -1524,7 +1594,7 @@ struct LaneSolver {
 // ---------------------------------------------------------------------------
 // One problem per calling thread: load inputs, run the solver, store the outputs.
 // ---------------------------------------------------------------------------
-template <int MODEL>
+template <int MODEL, int IG = 0>
 MPCR_D void lane_solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                                int trace_rows, double* ws) {
   const int N = cfg.N;
@@ -1564,15 +1634,21 @@ MPCR_D void lane_solve_problem(const Config& cfg, const BatchIn& in, const Batch
     const int ls = lam_g_stride(cfg);
     for (int k = 0; k < ls; ++k) so.lam_g[k] = 0.0;
   }
-  LaneSolver<MODEL> solver(cfg, prm, pv, ws);
+  LaneSolver<MODEL, IG> solver(cfg, prm, pv, ws);
   solver.solve(so);
 }
 
 MPCR_D void lane_solve_problem_any(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                                    int trace_rows, double* ws) {
-  if (cfg.model == kDynamic) lane_solve_problem<kDynamic>(cfg, in, out, b, trace_rows, ws);
-  else if (cfg.model == kKinematic) lane_solve_problem<kKinematic>(cfg, in, out, b, trace_rows, ws);
-  else lane_solve_problem<kBlended>(cfg, in, out, b, trace_rows, ws);
+  if (cfg.integrator == 0) {
+    if (cfg.model == kDynamic) lane_solve_problem<kDynamic, 0>(cfg, in, out, b, trace_rows, ws);
+    else if (cfg.model == kKinematic) lane_solve_problem<kKinematic, 0>(cfg, in, out, b, trace_rows, ws);
+    else lane_solve_problem<kBlended, 0>(cfg, in, out, b, trace_rows, ws);
+  } else {
+    if (cfg.model == kDynamic) lane_solve_problem<kDynamic, 1>(cfg, in, out, b, trace_rows, ws);
+    else if (cfg.model == kKinematic) lane_solve_problem<kKinematic, 1>(cfg, in, out, b, trace_rows, ws);
+    else lane_solve_problem<kBlended, 1>(cfg, in, out, b, trace_rows, ws);
+  }
 }
 
 }  // namespace mpcr

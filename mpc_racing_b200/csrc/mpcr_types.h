@@ -54,6 +54,7 @@ struct Config {
   int model;        // Model
   int wrap;         // keep the i=0 wrap-around rate rows of control/MPC.py:142-143
   int lane_con;     // enable the lane row commented out at control/MPC.py:135
+  int integrator;   // 0 = explicit Euler (reference), 1 = RK4 (extension; lane kernel only)
   Params p;
   IpmOptions o;
 };

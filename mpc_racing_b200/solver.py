@@ -51,7 +51,7 @@ class BatchedMPC:
                  runtime_params: Optional[RuntimeControllerParameters] = None,
                  wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
                  tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False,
-                 solve_kernel=0):
+                 solve_kernel=0, integrator="euler"):
         self.lib = _capi.load_library()
         fp = fixed_params or FixedControllerParameters()
         rp = runtime_params or RuntimeControllerParameters()
@@ -78,6 +78,8 @@ class BatchedMPC:
         cfg.acceptable_tol = float(acceptable_tol)
         # 0 = auto (by batch size), 1 = one problem per warp, 2 = one problem per lane
         cfg.solve_kernel = int({"auto": 0, "warp": 1, "lanes": 2}.get(solve_kernel, solve_kernel))
+        # "euler" = the reference's discretisation; "rk4" = extension, solved by the lane kernel
+        cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
         self.cfg = cfg
         self.N = cfg.N
         self.on_device = bool(on_device)

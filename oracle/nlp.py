@@ -58,7 +58,7 @@ class RacingNLP:
 
     def __init__(self, x0, u_prev, s0, cx, cy, params=None, N=None, Ts=None,
                  u_warm=None, model=V.MODEL_DYNAMIC, wrap=True, lane=False,
-                 max_error=None):
+                 max_error=None, integrator='euler'):
         p = dict(DEFAULT_PARAMS)
         if params:
             p.update(params)
@@ -66,6 +66,8 @@ class RacingNLP:
         self.N = N = int(p['N'] if N is None else N)
         self.Ts = Ts = float(p['Ts'] if Ts is None else Ts)
         self.model = model
+        # 'euler' = the maps control/MPC.py uses (parity); 'rk4' = extension (oracle/vehicle.py:rk4_step)
+        self.integrator = integrator
         self.wrap = bool(wrap)
         self.lane = bool(lane)
         self.max_error = max_error
@@ -172,7 +174,10 @@ class RacingNLP:
             w[self.iX(k, 0)] = x[k]
         for i in range(1, N + 1):
             w[self.iS(i)] = self.s0 + i * Ts * p['v_max']              # :127
-            x = V.f_dynamic(x, u_pred[:, i - 1], Ts)                   # :129 (always f_vehicle)
+            if self.integrator == 'rk4':
+                x = V.rk4_step(V.MODEL_DYNAMIC, x, u_pred[:, i - 1], Ts)
+            else:
+                x = V.f_dynamic(x, u_pred[:, i - 1], Ts)               # :129 (always f_vehicle)
             for k in range(6):
                 w[self.iX(k, i)] = x[k]
         self.w0 = w
@@ -263,12 +268,30 @@ class RacingNLP:
             g[self.iU(1, i - 1)] -= 2 * p['beta_delta'] * dst[i - 1]
         return g
 
+    # -- discretised model (Euler = reference; RK4 = extension) -----------------------------
+    def _step(self, X, U):
+        if self.integrator == 'rk4':
+            return V.rk4_step(self.model, X, U, self.Ts)
+        return V.f_model(self.model, X, U, self.Ts)
+
+    def _derivs(self, X, U, lam):
+        if self.integrator != 'rk4':
+            return V.model_derivs(self.model, X, U, self.Ts, lam)
+        J = np.zeros((X.shape[0], 6, 8))
+        H = np.zeros((X.shape[0], 8, 8)) if lam is not None else None
+        for i in range(X.shape[0]):
+            Ji, Hi = V.rk4_derivs(self.model, X[i], U[i], self.Ts, None if lam is None else lam[i])
+            J[i] = Ji
+            if lam is not None:
+                H[i] = Hi
+        return J, H
+
     # -- constraints ------------------------------------------------------------------
     def g(self, w):
         U, S, X = self.split(w)
         N = self.N
         out = self.Jlin @ w + self.goff
-        fx = V.f_model(self.model, X[:N], U, self.Ts)       # f(x_{i-1}, u_{i-1}), i = 1..N
+        fx = self._step(X[:N], U)                           # f(x_{i-1}, u_{i-1}), i = 1..N
         for i in range(1, N + 1):
             r = self.dyn_row[i]
             out[r:r + 6] -= fx[i - 1]
@@ -291,7 +314,7 @@ class RacingNLP:
         U, S, X = self.split(w)
         N = self.N
         J = self.Jlin.copy()
-        jm, _ = V.model_derivs(self.model, X[:N], U, self.Ts)
+        jm, _ = self._derivs(X[:N], U, None)
         for i in range(1, N + 1):
             r = self.dyn_row[i]
             cols = [self.iX(k, i - 1) for k in range(6)] + [self.iU(0, i - 1), self.iU(1, i - 1)]
@@ -324,7 +347,7 @@ class RacingNLP:
             H[a, c] -= b
             H[c, a] -= b
         lam_dyn = np.stack([lam[self.dyn_row[i]:self.dyn_row[i] + 6] for i in range(1, N + 1)])
-        _, hm = V.model_derivs(self.model, X[:N], U, self.Ts, lam_dyn)
+        _, hm = self._derivs(X[:N], U, lam_dyn)
         for i in range(1, N + 1):
             cols = [self.iX(k, i - 1) for k in range(6)] + [self.iU(0, i - 1), self.iU(1, i - 1)]
             H[np.ix_(cols, cols)] -= hm[i - 1]

@@ -214,3 +214,15 @@ def test_whole_batches_against_oracle_golden(name, kw, N):
     assert (du <= 1e-4).mean() >= 0.96, (du <= 1e-4).mean()
     # where the objective agrees, the inputs agree to the accuracy the termination tolerance allows
     assert du[rel <= 1e-6].max() <= 5e-3, du[rel <= 1e-6].max()
+
+
+def test_rk4_integrator_on_gpu(cfg2):
+    """RK4 extension: solved by the lane kernel; against the oracle with the same integrator."""
+    from mpc_racing_b200.solver import BatchedMPC
+    s = BatchedMPC(N=30, Ts=0.05, integrator="rk4")
+    idx = [0, 3, 7, 100]
+    res = _asdict(s.solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx]))
+    for j, b in enumerate(idx):
+        ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b],
+                           integrator='rk4')
+        assert_parity(res, j, ref)

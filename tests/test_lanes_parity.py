@@ -67,3 +67,22 @@ def test_lanes_variants(cfg2):
                     lanes=True)
     assert_parity(out, 0, oracle_solve(cfg2['x0'][3], None, cfg2['s0'][3], cfg2['cx'][3], cfg2['cy'][3],
                                        u_warm=cold['U'][0]))
+
+
+def test_rk4_integrator_nlp(cfg2):
+    """RK4 extension wired into the NLP (lane solver): same IPM, dynamics rows x+ = RK4(x, u);
+    against the oracle with the same integrator (oracle/vehicle.py:rk4_derivs)."""
+    idx = [0, 7]
+    out = emu_solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx],
+                    lanes=True, integrator=1)
+    for j, b in enumerate(idx):
+        ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b],
+                           integrator='rk4')
+        assert ref['status'] == 0
+        assert_parity(out, j, ref)
+    # the returned trajectory satisfies the RK4 dynamics, not the Euler ones
+    X, U = out['X'][0], out['U'][0]
+    f4 = np.stack([V.rk4_step(V.MODEL_DYNAMIC, X[:, i], U[:, i], 0.05) for i in range(30)], axis=1)
+    fe = V.f_dynamic(X[:, :-1].T, U.T, 0.05).T
+    assert np.abs(X[:, 1:] - f4).max() <= 1e-4
+    assert np.abs(X[:, 1:] - fe).max() > 1e-3

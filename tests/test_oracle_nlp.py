@@ -136,3 +136,29 @@ def test_initial_guess():
     U, _, _ = nlp.split(nlp.w0)
     np.testing.assert_array_equal(U[:-1, 0], uw[0, 1:])
     assert U[-1, 0] == uw[0, -1] and U[-1, 1] == uw[1, -1]
+
+
+def test_rk4_nlp_derivatives_by_finite_differences():
+    """NLP with the RK4 integrator (extension): Jacobian and Lagrangian Hessian against central
+    differences of g and of grad L."""
+    from mpc_racing_b200.workload import load_fixture
+    d = load_fixture("prod_t4_256.npz")
+    nlp = RacingNLP(d['x0'][2], d['u_prev'][2], d['s0'][2], d['cx'][2], d['cy'][2], N=6, Ts=0.05,
+                    integrator='rk4')
+    rng = np.random.default_rng(0)
+    w = nlp.w0 + 1e-2 * rng.normal(size=nlp.n)
+    lam = rng.normal(size=nlp.m)
+    J = nlp.jac(w)
+    H = nlp.hess(w, 0.0, lam)     # constraint part only: the cost's degree-4 polynomials in absolute
+    #                               progress (terms ~1e7) drown a finite-difference check in round-off
+    h = 1e-6
+    Jfd = np.zeros_like(J)
+    Hfd = np.zeros_like(H)
+    gl = lambda ww: nlp.jac(ww).T @ lam
+    for k in range(nlp.n):
+        e = np.zeros(nlp.n)
+        e[k] = h
+        Jfd[:, k] = (nlp.g(w + e) - nlp.g(w - e)) / (2 * h)
+        Hfd[:, k] = (gl(w + e) - gl(w - e)) / (2 * h)
+    assert np.abs(J - Jfd).max() <= 1e-6 * max(1.0, np.abs(J).max())
+    assert np.abs(H - Hfd).max() <= 1e-5 * max(1.0, np.abs(H).max())
