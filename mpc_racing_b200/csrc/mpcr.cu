@@ -122,6 +122,7 @@ struct mpcr_handle {
   double* d_lane_ws = nullptr;           // lane-kernel workspace, grown on demand
   size_t lane_ws_warps = 0;
   int last_blocks = 0, last_smem = 0;    // geometry of the last launch
+  int carve_env = -1, carve_now = 0;     // L1/shared carve-out: env override, value currently set
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // staging buffers for the host-pointer path
@@ -182,10 +183,11 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   h->smem_bytes = (h->stage_global ? kScratch : ws_doubles(h->cfg.N)) * (int)sizeof(double);
   CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   if (!h->stage_global) {
-    int carve = cudaSharedmemCarveoutMaxShared;
+    h->carve_env = -1;
     const char* e = getenv("MPCR_CARVEOUT");      // percent of the unified L1/shared array
-    if (e && atoi(e) > 0 && atoi(e) <= 100) carve = atoi(e);
-    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (e && atoi(e) > 0 && atoi(e) <= 100) h->carve_env = atoi(e);
+    h->carve_now = h->carve_env > 0 ? h->carve_env : (int)cudaSharedmemCarveoutMaxShared;
+    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carve_now));
   }
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, 32,
                                                    h->smem_bytes));
@@ -269,6 +271,21 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
   if (grid > B) grid = B;
   h->last_blocks = grid;
   h->last_smem = h->smem_bytes;
+  if (!h->stage_global && h->carve_env < 0) {
+    // Small batches leave shared memory unused: give it to L1, where the per-lane local-memory
+    // arrays live (measured: B = 1 3.99 -> 3.32 ms, B = 256 17.4 -> 14.4 ms).  Full grids keep the
+    // maximum shared carve-out (7 resident warps per SM).
+    const int resident = (grid + h->num_sms - 1) / h->num_sms;
+    int carve = (int)cudaSharedmemCarveoutMaxShared;
+    if (resident < h->blocks_per_sm) {
+      carve = (int)((100.0 * resident * (h->smem_bytes + 1024)) / (228.0 * 1024.0)) + 1;
+      if (carve > 100) carve = 100;
+    }
+    if (carve != h->carve_now) {
+      CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      h->carve_now = carve;
+    }
+  }
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   CK(cudaEventRecord(h->ev0, st));
   h->kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, h->d_slabs);
