@@ -32,7 +32,7 @@ template <int MODEL, bool STAGE_GLOBAL>
 __global__ void __launch_bounds__(32, MPCR_MIN_BLOCKS)
 solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
              int trace_rows, int* __restrict__ counter, double* __restrict__ slabs) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* stage = STAGE_GLOBAL ? slabs + (size_t)blockIdx.x * stage_doubles(cfg.N) : nullptr;
   while (true) {

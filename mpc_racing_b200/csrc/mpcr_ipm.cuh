@@ -73,19 +73,25 @@ MPCR_D bool finite_d(double v) { return v == v && fabs(v) < 1.0e300; }
 // Per-warp workspace (shared memory)
 // ---------------------------------------------------------------------------
 // stage storage layout (doubles)
+// Every block starts at an even offset and the stride is even, so that (with the 16-byte aligned
+// dynamic shared array) contiguous runs are loaded / stored as LDS.128 / STS.128.
 constexpr int kOffA = 0;        // StageLin (21)
-constexpr int kOffB = 21;       // b = -c_{k+1}  (6)
-constexpr int kOffHs = 27;      // packed sparse stage Hessian (32)
-constexpr int kOffGs = 59;      // dense stage gradient over (z, w) (12); gs[2] is always 0
+constexpr int kOffBase0 = 21;   // derivative part of (thr,thr) (the entry also carries row terms)
+constexpr int kOffB = 22;       // b = -c_{k+1}  (6)
+constexpr int kOffHs = 28;      // packed sparse stage Hessian (32)
+constexpr int kOffGs = 60;      // dense stage gradient over (z, w) (12); gs[2] is always 0
 constexpr int kZeroSlot = 34;   // = kOffGs + 2 relative to kOffHs: the always-zero slot
-constexpr int kOffK = 71;       // feedback gain (3 x 9); reused for the forward-sweep results
-constexpr int kOffKf = 98;      // feed-forward, 3 right-hand sides (3 x 3)
-constexpr int kOffBase = 107;   // derivative part of (thr,thr), (st,st) (these also carry row terms)
-constexpr int kStride = 109;    // odd: conflict-free lane-parallel writes
+constexpr int kOffK = 72;       // feedback gain (3 x 9); reused for the forward-sweep results
+constexpr int kOffBase1 = 99;   // derivative part of (st,st)
+constexpr int kOffKf = 100;     // feed-forward, 3 right-hand sides (3 x 3)
+constexpr int kStride = 110;    // even (alignment); lane-parallel writes then see 4-way bank conflicts,
+                                // ~120 stores per iteration - negligible next to the Riccati loads
 constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
+constexpr int kPS = 10;         // row stride of the 9x9 cost-to-go matrix (even: aligned rows)
 
 constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
-constexpr int kScratch = 81 + 108 + 144 + 27 + 27 + 36 + kMisc;
+constexpr int kScrP = 0, kScrT = 90, kScrG = 198, kScrPv = 342, kScrTv = 370, kScrGv = 398, kScrMisc = 434;
+constexpr int kScratch = kScrMisc + kMisc;
 MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
 MPCR_HD int stage_doubles(int N) { return (N + 1) * kStride; }
 
@@ -100,7 +106,7 @@ struct WarpWs {
   int soff_;       // offset of the scratch area inside the shared/host workspace
   MPCR_D double* sm() const {
 #if defined(__CUDA_ARCH__)
-    extern __shared__ double mpcr_dyn_smem[];
+    extern __shared__ __align__(16) double mpcr_dyn_smem[];
     return mpcr_dyn_smem;
 #else
     return base_;
@@ -111,13 +117,13 @@ struct WarpWs {
     stage_ = stage_base;
     soff_ = SG ? 0 : (N + 1) * kStride;
   }
-  MPCR_D double* P() const { return sm() + soff_; }            // [9][9]
-  MPCR_D double* T() const { return sm() + soff_ + 81; }       // [9][12]
-  MPCR_D double* G() const { return sm() + soff_ + 189; }      // [12][12]
-  MPCR_D double* pv() const { return sm() + soff_ + 333; }     // [3][9]
-  MPCR_D double* tv() const { return sm() + soff_ + 360; }     // [3][9]
-  MPCR_D double* gv() const { return sm() + soff_ + 387; }     // [3][12]
-  MPCR_D double* misc() const { return sm() + soff_ + 423; }   // [kMisc]
+  MPCR_D double* P() const { return sm() + soff_ + kScrP; }    // [9][kPS]
+  MPCR_D double* T() const { return sm() + soff_ + kScrT; }       // [9][12]
+  MPCR_D double* G() const { return sm() + soff_ + kScrG; }      // [12][12]
+  MPCR_D double* pv() const { return sm() + soff_ + kScrPv; }     // [3][9]
+  MPCR_D double* tv() const { return sm() + soff_ + kScrTv; }     // [3][9]
+  MPCR_D double* gv() const { return sm() + soff_ + kScrGv; }     // [3][12]
+  MPCR_D double* misc() const { return sm() + soff_ + kScrMisc; }   // [kMisc]
   MPCR_D double* st(int k) const { return (SG ? stage_ : sm()) + k * kStride; }   // [(N+1)][kStride]
 };
 
@@ -445,15 +451,14 @@ struct WarpSolver {
       for (int i = 0; i < 3; ++i)
         for (int k = 0; k < 2; ++k) st[kOffA + 15 + 2 * i + k] = lin.bu[i][k];
       double* hs = st + kOffHs;
-      double* base = st + kOffBase;
       // (thr,thr), (st,st) also receive row terms: their derivative part is kept in `base`;
       // the (X,Y,s) block's derivative part stays in registers (hcp6)
       for (int k = 0; k < 6; ++k) hcp6[k] = hcp[k];
       for (int k = 0; k < kHmDoubles; ++k) hs[6 + k] = (mode == 0) ? -hm[k] : 0.0;
       hs[6 + hm_idx(1, 1)] += hcp[6];
       hs[6 + hm_idx(2, 2)] += hcp[7];
-      base[0] = hs[6 + hm_idx(4, 4)];
-      base[1] = hs[6 + hm_idx(5, 5)];
+      st[kOffBase0] = hs[6 + hm_idx(4, 4)];
+      st[kOffBase1] = hs[6 + hm_idx(5, 5)];
       if (lane == N - 1) {
         double* hN = ws.st(N) + kOffHs;
         double* bN = ws.st(N) + kOffK;          // the terminal stage has no gain: free space
@@ -547,7 +552,6 @@ struct WarpSolver {
     double* st = ws.st(lane);
     double* hs = st + kOffHs;
     double* gs = st + kOffGs;
-    const double* base = st + kOffBase;
     const double dthr = wrap0 ? 0.0 : Dthr;
     const double dst = wrap0 ? 0.0 : Dst;
     // (X, Y, s) block of state `lane`: derivative part + lane-row Sigma term D gC gC'
@@ -557,8 +561,8 @@ struct WarpSolver {
     hs[3] = hcp6[3] + Dlane_p * gCp[1] * gCp[1];
     hs[4] = hcp6[4] + Dlane_p * gCp[1] * gCp[2];
     hs[5] = hcp6[5] + Dlane_p * gCp[2] * gCp[2];
-    hs[6 + hm_idx(4, 4)] = base[0] + Rtt + dthr;
-    hs[6 + hm_idx(5, 5)] = base[1] + Rss + dst + bq;
+    hs[6 + hm_idx(4, 4)] = st[kOffBase0] + Rtt + dthr;
+    hs[6 + hm_idx(5, 5)] = st[kOffBase1] + Rss + dst + bq;
     hs[27] = Dprog;
     hs[28] = dthr;
     hs[29] = dst + bq;
@@ -639,7 +643,7 @@ struct WarpSolver {
         int e = lane + 32 * j;
         if (e < 81) {
           int r = e / 9, c = e % 9;
-          P[e] = stage_entry(stN, slot_of(r, c), dw);
+          P[r * kPS + c] = stage_entry(stN, slot_of(r, c), dw);
         }
       }
       if (lane < 27) {
@@ -656,7 +660,7 @@ struct WarpSolver {
       // ---- round 1: T = P M (rows), t_j = p_j + P b_j -----------------------------
       if (lane < 9) {
         double pr[9], A[21], out[12];
-        for (int c = 0; c < 9; ++c) pr[c] = P[lane * 9 + c];
+        for (int c = 0; c < 9; ++c) pr[c] = P[lane * kPS + c];
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(pr, A, Ts, out);
         for (int c = 0; c < 12; ++c) T[lane * 12 + c] = out[c];
@@ -728,7 +732,7 @@ struct WarpSolver {
         kdst[kstride] = k1;
         kdst[2 * kstride] = k2;
         double* pdst = isvec ? (ws.pv() + j * 9) : (P + c);
-        const int pstride = isvec ? 1 : 9;
+        const int pstride = isvec ? 1 : kPS;
 #pragma unroll
         for (int a = 0; a < 9; ++a)
           pdst[a * pstride] = src[a * sstride] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
