@@ -281,10 +281,10 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
       carve = (int)((100.0 * resident * (h->smem_bytes + 1024)) / (228.0 * 1024.0)) + 1;
       if (carve > 100) carve = 100;
     }
-    if (carve != h->carve_now) {
-      CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      h->carve_now = carve;
-    }
+    // set on every launch: the attribute belongs to the kernel function, not to this handle
+    // (another handle may have changed it)
+    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    h->carve_now = carve;
   }
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   CK(cudaEventRecord(h->ev0, st));
