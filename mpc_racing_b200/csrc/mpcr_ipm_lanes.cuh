@@ -90,6 +90,22 @@ struct LaneWs {
   MPCR_HD double& operator()(int e) const { return p[(size_t)e * kLaneStride]; }
   MPCR_HD double& s(int k, int f) const { return p[(size_t)(k * lw::REC + f) * kLaneStride]; }
   MPCR_HD double& t(int N, int f) const { return p[(size_t)(N * lw::REC + f) * kLaneStride]; }
+  // Prefetch elements [f, f + n) of stage k into L1 (a warp-wide prefetch covers the element's
+  // 256-byte row).  The lane kernel runs ~1 warp per scheduler, so nothing else hides the HBM
+  // latency of its workspace: every pass asks for the NEXT stage's inputs before it starts on the
+  // current one.
+  MPCR_HD void pf(int k, int f, int n) const {
+#if defined(__CUDA_ARCH__) && !defined(MPCR_LANE_NO_PREFETCH)
+#pragma unroll 4
+    for (int i = 0; i < n; ++i)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)(k * lw::REC + f + i) * kLaneStride));
+#else
+    (void)k; (void)f; (void)n;
+#endif
+  }
+  MPCR_HD void pf_rows(int k, int first_array, int n_arrays) const {   // rows 0..6 of consecutive row arrays
+    for (int a = 0; a < n_arrays; ++a) pf(k, first_array + a * kNumRows, 7);
+  }
 };
 
 // packed symmetric 9x9 (upper triangle, row-major)
@@ -391,6 +407,7 @@ struct LaneSolver {
     const double bd2 = 2.0 * p.beta_delta;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
+      if (k + 1 < N) { w.pf(k + 1, lw::X, 27); w.pf_rows(k + 1, lw::RS, 5); }
       const unsigned m = rowmask(k);
       double xk[6], uk[2], lamk[6];
       for (int a = 0; a < 6; ++a) xk[a] = w.s(k, lw::X + a);
@@ -676,6 +693,8 @@ struct LaneSolver {
     bool ok = true;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
+      if (k >= 1) { w.pf(k - 1, lw::CRES, 6); w.pf(k - 1, lw::A, NA); w.pf(k - 1, lw::HSD, 27 + 9); }
+      if (k >= 2) { w.pf_rows(k - 2, lw::RS, 1); w.pf_rows(k - 2, lw::RVL, 3); w.pf(k - 2, lw::GC, 9); }
       // rows of this stage are in q; the lane row of state k belongs to stage k-1
       double Dlane_p = 0.0, elane_p = 0.0;
       double gcp[5] = {0, 0, 0, 0, 0}, gCp[3] = {0, 0, 0};
@@ -877,6 +896,7 @@ struct LaneSolver {
       for (int a = 0; a < 9; ++a) z[j][a] = 0.0;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
+      if (k + 1 < N) { w.pf(k + 1, lw::CRES, 6); w.pf(k + 1, lw::A, NA); w.pf(k + 1, lw::K, 36); }
       double A[kLinRk4], Kk[27];
       for (int a = 0; a < NA; ++a) A[a] = w.s(k, lw::A + a);
       for (int a = 0; a < 27; ++a) Kk[a] = w.s(k, lw::K + a);
@@ -960,6 +980,11 @@ struct LaneSolver {
     double a_pr = 1.0, a_du = 1.0, gsds = 0.0, gfd = 0.0, th = 0.0;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
+      if (k >= 1) {
+        w.pf(k - 1, lw::HS, 32 + 7); w.pf(k - 1, lw::A, NA); w.pf(k - 1, lw::GC, 9); w.pf(k - 1, lw::CRES, 12);
+        w.pf_rows(k - 1, lw::RS, 5);
+      }
+      if (k >= 2) w.pf(k - 2, lw::Z3, 27);
       const unsigned m = rowmask(k);
       // new multipliers of the dynamics rows of stage k: -pi_{k+1}
       for (int a = 0; a < 6; ++a) w.s(k, lw::NLAM + a) = -pi[a];
@@ -1071,6 +1096,7 @@ struct LaneSolver {
     bool fin = true;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
+      if (k + 1 < N) { w.pf(k + 1, lw::X, 9); w.pf(k + 1, lw::DCS, 15); w.pf_rows(k + 1, lw::RS, 1); w.pf_rows(k + 1, lw::RDSR, 1); }
       const unsigned m = rowmask(k);
       double tx[6], tu[2];
       for (int a = 0; a < 6; ++a) tx[a] = w.s(k, lw::X + a) + at * w.s(k, lw::DX + a);
@@ -1491,6 +1517,7 @@ struct LaneSolver {
       const double az = a_du;
 #pragma unroll 1
       for (int k = 0; k < N; ++k) {
+        if (k + 1 < N) { w.pf(k + 1, lw::X, 48); w.pf_rows(k + 1, lw::RS, 4); w.pf_rows(k + 1, lw::RDSR, 3); }
         const unsigned m = rowmask(k);
         for (int a = 0; a < 6; ++a) {
           w.s(k, lw::X + a) += astep * w.s(k, lw::DX + a);
