@@ -369,6 +369,7 @@ static int solve_impl(mpcr_handle* h, int B, const double* x0, const double* u_p
   if (max_err) CK(h2d(d_me, max_err, B));
   if (params) CK(h2d(d_pr, params, (size_t)B * 5));
   if (u_warm) CK(h2d(d_uw, u_warm, (size_t)B * 2 * N));
+  if (trace) CK(cudaMemsetAsync(d_tr, 0, ntr * sizeof(double), st));   // rows past the last iteration stay 0
   BatchIn in{d_x0, d_up, d_s0, d_cx, d_cy, max_err ? d_me : nullptr, params ? d_pr : nullptr,
              u_warm ? d_uw : nullptr};
   BatchOut out{d_U, d_X, d_S, d_eC, d_eL, lam_g ? d_lam : nullptr, d_obj, d_status, d_iters, d_tr};
