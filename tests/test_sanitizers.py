@@ -1,0 +1,57 @@
+"""Memory-safety of the solver sources: both solvers (warp-per-problem through the SIMT emulator,
+lane-per-problem natively) are compiled for the host with AddressSanitizer + UBSan and run over the
+shape variants (horizons 2/15/32, models, lane rows, no wrap rows, warm start, RK4).  The same source
+is what nvcc compiles for the device (compute-sanitizer is not available on the GPU pool)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+DRIVER = r'''
+import sys; sys.path.insert(0, %(tests)r); sys.path.insert(0, %(root)r)
+import ctypes as C, numpy as np
+import emu_util
+from mpc_racing_b200._capi import MpcrConfig
+l = C.CDLL(%(lib)r)
+emu_util._lib = l
+l.emu_config_default.argtypes = [C.POINTER(MpcrConfig)]
+l.emu_lam_g_stride.argtypes = [C.POINTER(MpcrConfig)]
+l.emu_solve_batch.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
+l.emu_solve_batch_lanes.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
+from emu_util import emu_solve
+from mpc_racing_b200.workload import load_fixture
+d = load_fixture(); d3 = load_fixture("cfg3_t1_triple_512.npz")
+idx = [0, 7]
+a = lambda k: d[k][idx]
+for lanes in (False, True):
+    for kw in (dict(), dict(N=32), dict(N=2), dict(N=15), dict(wrap_constraint=0), dict(model=2)):
+        r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), lanes=lanes, trace=True, **kw)
+        assert (r['status'] == 0).all(), (lanes, kw, r['status'])
+    r = emu_solve(d3['x0'][:1], d3['u_prev'][:1], d3['s0'][:1], d3['cx'][:1], d3['cy'][:1],
+                  max_err=d3['max_err'][:1], lane_constraint=1, lanes=lanes)
+    r = emu_solve(a('x0'), np.full((2, 2), np.nan), a('s0'), a('cx'), a('cy'), lanes=lanes,
+                  u_warm=np.zeros((2, 2, 30)))
+r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), lanes=True, integrator=1)
+print("SANITIZED RUN OK")
+'''
+
+
+def test_solver_sources_under_asan_ubsan(tmp_path):
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    ubsan = subprocess.run(["gcc", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+    if not (os.path.isabs(asan) and os.path.exists(asan) and os.path.exists(ubsan)):
+        pytest.skip("libasan / libubsan not installed")
+    lib = str(tmp_path / "libmpcr_emu_asan.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-fsanitize=address,undefined",
+                           "-fno-omit-frame-pointer", "-o", lib, os.path.join(HERE, "emu", "emu_main.cpp")])
+    env = dict(os.environ, LD_PRELOAD=asan + ":" + ubsan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+               UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    out = subprocess.run([sys.executable, "-c", DRIVER % dict(tests=HERE, root=ROOT, lib=lib)], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "SANITIZED RUN OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+    assert "runtime error" not in out.stderr and "AddressSanitizer" not in out.stderr.replace(
+        "ASan doesn't fully support makecontext", ""), out.stderr[-3000:]
