@@ -52,6 +52,26 @@ def test_invalid_config_is_rejected(field, value):
     assert not h
 
 
+@pytest.mark.parametrize("lanes", [False, True])
+def test_pathological_inputs_terminate_with_failure_codes(cfg2, lanes):
+    """NaN / Inf / singular inputs never hang or poison neighbours: each problem ends with a failure
+    status (control/MPC.py:172-181 convention: last iterate, sol = None)."""
+    from emu_util import emu_solve
+    idx = [0, 1, 2, 3, 4, 5]
+    x0, s0, cx = cfg2['x0'][idx].copy(), cfg2['s0'][idx].copy(), cfg2['cx'][idx].copy()
+    x0[0, 3] = np.nan                  # NaN speed
+    x0[1, 0] = np.inf                  # infinite position
+    cx[2, :] = np.nan                  # NaN centerline coefficients
+    x0[4, 3] = 0.0
+    x0[4, 4] = 0.0                     # |v| = 0: the steering-gain derivative divides by it
+    s0[5] = 1e9                        # absurd progress
+    r = emu_solve(x0, cfg2['u_prev'][idx], s0, cx, cfg2['cy'][idx], lanes=lanes, max_iter=60)
+    assert list(r['status'][:3]) == [-4, -4, -4]            # Invalid_Number_Detected
+    assert r['status'][3] == 0                               # the untouched neighbour converges
+    assert r['status'][4] < 0 and r['status'][5] < 0
+    assert (r['iters'] <= 60).all()
+
+
 # ---- GPU: through the C ABI ------------------------------------------------------------------
 @pytest.mark.gpu
 def test_empty_batch_and_null_arguments(cfg2):
