@@ -52,6 +52,8 @@ DEFAULT_OPTIONS = dict(
     # inertia correction
     delta_w_init=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_minus=1.0 / 3.0, kappa_w_plus=8.0, kappa_w_plus_first=100.0,
+    # EXPERIMENTAL (study only, not mirrored by the kernels): IPOPT's restoration phase, oracle/restoration.py
+    restoration=False, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True,
 )
 
 
@@ -137,7 +139,7 @@ class _KKT:
         return dx, ds, dyc, dyd
 
 
-def solve(nlp, options=None, trace=None):
+def solve(nlp, options=None, trace=None, stop=None):
     o = dict(DEFAULT_OPTIONS)
     if options:
         o.update(options)
@@ -257,6 +259,7 @@ def solve(nlp, options=None, trace=None):
     res = Result()
     n_fact = 0
     ls_total = 0
+    n_resto = 0
 
     while True:
         gf = df * nlp.grad_f(x)
@@ -264,6 +267,9 @@ def solve(nlp, options=None, trace=None):
         if not (np.all(np.isfinite(gf)) and np.all(np.isfinite(Jc)) and np.all(np.isfinite(Jd))
                 and np.isfinite(fval)):
             status = INVALID_NUMBER
+            break
+        if stop is not None and it > 0 and stop(x, s):
+            status = SOLVE_SUCCEEDED
             break
         # ---- convergence tests --------------------------------------------------
         E0, dual_inf, pr_inf, compl0 = errors(0.0, gf, Jc, Jd, c, d, s, yc, yd, vL, vU)
@@ -444,6 +450,54 @@ def solve(nlp, options=None, trace=None):
                     break
             alpha *= o['alpha_red_factor']
         ls_total += n_ls
+        if not accepted and o['restoration']:
+            from .restoration import RestoNLP
+            theta_R, phi_R = theta, phi
+            filt.append(((1 - o['gamma_theta']) * theta_R, phi_R - o['gamma_phi'] * theta_R))
+            cfun = lambda xx: dc_s * (nlp.g(xx)[ic] - cval)
+            dfun = lambda xx: dd_s * nlp.g(xx)[idn]
+
+            def hess_con(xx, yc_, yd_):
+                lam_ = np.zeros(m)
+                lam_[ic] = yc_ * dc_s
+                lam_[idn] = yd_ * dd_s
+                return nlp.hess(xx, 0.0, lam_)
+            mu_R = max(mu, float(np.max(np.abs(np.concatenate([c, d - s])), initial=0.0)))
+            rn = RestoNLP(n, cfun, dfun, jacs, hess_con, dL, dU, x, s, mu_R, relax_eq=o['resto_relax_eq'])
+            found = {}
+
+            def resto_stop(w, s_in):
+                xx = w[:n]
+                ss = s_in[:md]
+                fv, cc, dd = evals(xx)
+                th = theta_of(cc, dd, ss)
+                if not (np.isfinite(fv) and th <= o['kappa_resto'] * theta_R and th <= theta_max):
+                    return False
+                ph = barrier_obj(fv, ss, mu)
+                if not (np.isfinite(ph) and acceptable_to_filter(th, ph)):
+                    return False
+                found.update(x=xx.copy(), s=ss.copy())
+                return True
+            ro = dict(o)
+            ro.update(restoration=False, nlp_scaling_max_gradient=1e300, mu_init=mu_R, max_iter=o['resto_max_iter'],
+                      tol=1e-12, acceptable_tol=1e-12)
+            rr = solve(rn, ro, stop=resto_stop)
+            n_resto += rr.iters
+            if found:
+                x, s = found['x'], found['s']
+                fval, c, d = evals(x)
+                vL = np.where(hasL, o['bound_mult_init_val'], 0.0)
+                vU = np.where(hasU, o['bound_mult_init_val'], 0.0)
+                gf = df * nlp.grad_f(x)
+                Jc, Jd = jacs(x)
+                kk = _KKT(np.zeros((n, n)), Jc, Jd, np.zeros(md), 1.0)
+                _, _, yc, yd = kk.solve(gf, vU - vL, np.zeros(mc), np.zeros(md))
+                yc, yd = -yc, -yd
+                if max(np.max(np.abs(yc), initial=0.0), np.max(np.abs(yd), initial=0.0)) > o['constr_mult_init_max']:
+                    yc[:] = 0.0
+                    yd[:] = 0.0
+                it += rr.iters
+                continue
         if not accepted:
             status = RESTORATION_NEEDED
             break
@@ -475,5 +529,6 @@ def solve(nlp, options=None, trace=None):
     res.df = df
     res.n_fact = n_fact
     res.ls_total = ls_total
+    res.n_resto = n_resto
     res.success = status in (SOLVE_SUCCEEDED, SOLVED_TO_ACCEPTABLE_LEVEL)
     return res
