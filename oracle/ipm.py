@@ -53,7 +53,7 @@ DEFAULT_OPTIONS = dict(
     delta_w_init=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_minus=1.0 / 3.0, kappa_w_plus=8.0, kappa_w_plus_first=100.0,
     # EXPERIMENTAL (study only, not mirrored by the kernels): IPOPT's restoration phase, oracle/restoration.py
-    restoration=False, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True,
+    restoration=False, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True, resto_quad_weight=1.0,
 )
 
 
@@ -463,12 +463,16 @@ def solve(nlp, options=None, trace=None, stop=None):
                 lam_[idn] = yd_ * dd_s
                 return nlp.hess(xx, 0.0, lam_)
             mu_R = max(mu, float(np.max(np.abs(np.concatenate([c, d - s])), initial=0.0)))
-            rn = RestoNLP(n, cfun, dfun, jacs, hess_con, dL, dU, x, s, mu_R, relax_eq=o['resto_relax_eq'])
+            if o['restoration'] == 'quad':
+                from .restoration import RestoQuadNLP
+                rn = RestoQuadNLP(n, cfun, dfun, jacs, hess_con, dL, dU, x, s, mu_R, weight=o['resto_quad_weight'])
+            else:
+                rn = RestoNLP(n, cfun, dfun, jacs, hess_con, dL, dU, x, s, mu_R, relax_eq=o['resto_relax_eq'])
             found = {}
 
             def resto_stop(w, s_in):
                 xx = w[:n]
-                ss = s_in[:md]
+                ss = w[n:n + md] if o['restoration'] == 'quad' else s_in[:md]
                 fv, cc, dd = evals(xx)
                 th = theta_of(cc, dd, ss)
                 if not (np.isfinite(fv) and th <= o['kappa_resto'] * theta_R and th <= theta_max):

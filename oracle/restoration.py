@@ -87,3 +87,64 @@ class RestoNLP:
         H[:n, :n] = self.hess_con(w[:n], lam[:mc], lam[mc:mc + md])
         H[np.arange(n), np.arange(n)] += sigma_f * self.zeta * self.DR2
         return H
+
+
+class RestoQuadNLP:
+    """Variant studied for the kernels: no elastic variables.  The inequality rows' defining
+    equations d(x) - s = 0 are replaced by a quadratic penalty,
+
+        min  w/2 * || d(x) - s ||^2 + zeta/2 * || D_R (x - x_R) ||^2
+        s.t. c(x) = 0,   dL <= s <= dU
+
+    over the SAME variables (x, s) as the original problem, so every row keeps its single slack and
+    the stage-wise elimination only changes its (D_r, e_r) formulas."""
+
+    def __init__(self, n, cfun, dfun, jacs, hess_con, dL, dU, x_R, s_R, mu, weight=1.0):
+        c0 = cfun(x_R)
+        self.nx, self.mc, self.md = n, c0.size, s_R.size
+        self.cfun, self.dfun, self.jacs, self.hess_con = cfun, dfun, jacs, hess_con
+        self.wq = weight
+        self.zeta = np.sqrt(mu)
+        self.x_R = x_R.copy()
+        self.DR2 = (1.0 / np.maximum(1.0, np.abs(x_R))) ** 2
+        self.n = n + self.md
+        self.m = self.mc + self.md
+        self.gl = np.concatenate([np.zeros(self.mc), dL])
+        self.gu = np.concatenate([np.zeros(self.mc), dU])
+        self.w0 = np.concatenate([x_R, s_R])
+
+    def f(self, w):
+        x, s = w[:self.nx], w[self.nx:]
+        r = self.dfun(x) - s
+        dx = x - self.x_R
+        return 0.5 * self.wq * r @ r + 0.5 * self.zeta * np.sum(self.DR2 * dx * dx)
+
+    def grad_f(self, w):
+        x, s = w[:self.nx], w[self.nx:]
+        r = self.dfun(x) - s
+        _, Jd = self.jacs(x)
+        return np.concatenate([self.wq * Jd.T @ r + self.zeta * self.DR2 * (x - self.x_R), -self.wq * r])
+
+    def g(self, w):
+        return np.concatenate([self.cfun(w[:self.nx]), w[self.nx:]])
+
+    def jac(self, w):
+        n, mc, md = self.nx, self.mc, self.md
+        Jc, _ = self.jacs(w[:n])
+        J = np.zeros((self.m, self.n))
+        J[:mc, :n] = Jc
+        J[mc:, n:] = np.eye(md)
+        return J
+
+    def hess(self, w, sigma_f, lam):
+        n, mc, md = self.nx, self.mc, self.md
+        x, s = w[:n], w[n:]
+        r = self.dfun(x) - s
+        _, Jd = self.jacs(x)
+        H = np.zeros((self.n, self.n))
+        H[:n, :n] = self.hess_con(x, lam[:mc], sigma_f * self.wq * r) + sigma_f * self.wq * Jd.T @ Jd
+        H[np.arange(n), np.arange(n)] += sigma_f * self.zeta * self.DR2
+        H[:n, n:] = -sigma_f * self.wq * Jd.T
+        H[n:, :n] = -sigma_f * self.wq * Jd
+        H[n + np.arange(md), n + np.arange(md)] += sigma_f * self.wq
+        return H
