@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MPCR_VERSION 101
+#define MPCR_VERSION 102
 
 /* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
  * models/BlendedBicycleModel.py:23-46 blend of the two) */
@@ -91,6 +91,10 @@ typedef struct mpcr_config {
   int32_t solve_kernel;      /* MPCR_KERNEL_* (0 = auto) */
   int32_t integrator;        /* MPCR_INTEGRATOR_EULER (reference, default) or MPCR_INTEGRATOR_RK4 (extension;
                               * solved by the lane kernel) */
+  int32_t restoration;       /* 1: when the filter line search fails, run the feasibility-restoration phase
+                              * (IPOPT would; quadratic-penalty variant) instead of returning
+                              * MPCR_RESTORATION_FAILED.  Implemented by the lane kernel. 0 = off (default) */
+  int32_t reserved_;
 } mpcr_config;
 
 typedef struct mpcr_handle mpcr_handle;

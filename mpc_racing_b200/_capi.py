@@ -31,6 +31,7 @@ class MpcrConfig(C.Structure):
         ("dual_inf_tol", C.c_double), ("constr_viol_tol", C.c_double),
         ("compl_inf_tol", C.c_double), ("mu_init", C.c_double),
         ("solve_kernel", C.c_int32), ("integrator", C.c_int32),
+        ("restoration", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

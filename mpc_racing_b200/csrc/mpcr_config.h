@@ -42,6 +42,8 @@ inline void config_default(mpcr_config* c) {
   c->mu_init = 0.1;
   c->solve_kernel = MPCR_KERNEL_AUTO;
   c->integrator = MPCR_INTEGRATOR_EULER;
+  c->restoration = 0;
+  c->reserved_ = 0;
 }
 
 inline void config_convert(const mpcr_config& c, Config* out) {
@@ -115,6 +117,10 @@ inline void config_convert(const mpcr_config& c, Config* out) {
   o.kappa_w_minus = 1.0 / 3.0;
   o.kappa_w_plus = 8.0;
   o.kappa_w_plus_first = 100.0;
+  o.restoration = c.restoration;
+  o.resto_max_iter = 200;
+  o.resto_weight = 1.0;
+  o.kappa_resto = 0.9;
 }
 
 inline bool config_valid(const mpcr_config& c, const char** why) {
@@ -125,6 +131,7 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.n_exp < 1.0) { *why = "n_exp must be >= 1"; return false; }
   if (c.solve_kernel < 0 || c.solve_kernel > 2) { *why = "unknown solve_kernel"; return false; }
   if (c.integrator < 0 || c.integrator > 1) { *why = "unknown integrator"; return false; }
+  if (c.restoration < 0 || c.restoration > 1) { *why = "restoration must be 0 or 1"; return false; }
   if (c.integrator == MPCR_INTEGRATOR_RK4 && c.solve_kernel == MPCR_KERNEL_WARP) {
     *why = "the RK4 integrator is implemented by the lane kernel only";
     return false;

@@ -73,14 +73,18 @@ constexpr int SVD = DSOC + kNumRows;    // saved plain step (9), its slack steps
 constexpr int SVDSR = SVD + 9;
 constexpr int SVLAM = SVDSR + kNumRows;
 constexpr int SVDYD = SVLAM + 6;
-constexpr int REC = SVDYD + kNumRows;
+constexpr int XR = SVDYD + kNumRows;    // restoration: reference point x_R (x (6), s_hat, u (2))
+constexpr int PG = XR + 9;              // restoration: gradient of the proximity term over the same 9 variables
+constexpr int REC = PG + 9;
 // per-problem tail after the N stage records
 constexpr int T_HSD = 0;                // terminal stage: derivative part (27)
 constexpr int T_HS = 27;                // assembled (32)
 constexpr int T_GS = 59;                // (12)
 constexpr int T_FTH = 71;               // filter (32 + 32)
 constexpr int T_FPH = 103;
-constexpr int TAIL = 135;
+constexpr int T_FTH2 = 135;             // the restoration phase's own filter
+constexpr int T_FPH2 = 167;
+constexpr int TAIL = 199;
 }  // namespace lw
 
 MPCR_HD int lane_ws_doubles(int N) { return N * lw::REC + lw::TAIL; }
@@ -250,6 +254,11 @@ struct LaneSolver {
   int n_eq_ineq, n_bounds;
   double Dw[2];
   int filt_n;
+  // feasibility restoration (quadratic-penalty variant): while `resto` is set the
+  // objective is  wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2, the rows' multipliers are yd = wq (d - s)
+  bool resto;
+  double wq, zeta;
+  int fbase_th, fbase_ph;   // filter arrays in use (outer / restoration)
 
   MPCR_D LaneSolver(const Config& c, const Params& prm, const ProblemView& pv, double* ws)
       : cfg(c), p(prm), o(c.o), pb(pv), w{ws}, N(c.N) {}
@@ -388,14 +397,15 @@ struct LaneSolver {
   // mode also the optimality error; in Init mode the gradient-based scaling factors.
   //   mode 0: Newton (exact Hessian), mode 1: least-squares multiplier init
   // -------------------------------------------------------------------------
-  MPCR_D void pass_derivs(int mode, Errors& er, double& gmax_out, double& ddl_out) {
+  // keep_scaling: mode-1 evaluation that leaves the row scaling untouched (multiplier re-init after restoration)
+  MPCR_D void pass_derivs(int mode, Errors& er, double& gmax_out, double& ddl_out, bool keep_scaling) {
     const double Ts = cfg.Ts;
     double xp[6], shp = pb.s0, up[2];
     for (int a = 0; a < 6; ++a) xp[a] = pb.x0[a];
     up[0] = w.s(N - 1, lw::U);
     up[1] = w.s(N - 1, lw::U + 1);
-    double hcp[8];
-    for (int a = 0; a < 8; ++a) hcp[a] = 0.0;
+    double hcp[10];
+    for (int a = 0; a < 10; ++a) hcp[a] = 0.0;
     // carried quantities of stage k-1 for the dual infeasibility of state k / input k-1
     double gxp[6], lamp[6], gsp = 0.0, yprog_p = 0.0, ru0p = 0.0, ru1p = 0.0, sigc_p = 0.0;
     for (int a = 0; a < 6; ++a) { gxp[a] = 0.0; lamp[a] = 0.0; }
@@ -427,11 +437,34 @@ struct LaneSolver {
       gcost[3] = df * sc.gvx;
       gcost[4] = df * sc.gvy;
       for (int a = 0; a < 3; ++a) gC[a] = ddl * sc.gC[a];
-      const double sigc = (k >= 1) ? (uk[1] - up[1]) : 0.0;
-      double hc[8];
-      for (int a = 0; a < 8; ++a) hc[a] = 0.0;
+      const double sigc = (k >= 1 && !resto) ? (uk[1] - up[1]) : 0.0;
+      double hc[10];            // cost Hessian of state k+1: (X,Y,s) block (6), v_x, v_y, [restoration: yaw, r]
+      for (int a = 0; a < 10; ++a) hc[a] = 0.0;
       const double ydl = on(m, kLane) ? w.s(k, lw::RYD + kLane) : 0.0;
-      if (mode == 0) {
+      double pgr[9], pdu[2] = {0.0, 0.0};
+      for (int a = 0; a < 9; ++a) pgr[a] = 0.0;
+      if (resto) {
+        // proximity term zeta/2 |D_R (v - v_R)|^2 over (x_{k+1}, s_{k+1}, u_k) replaces the cost
+        const double v9[9] = {xk[0], xk[1], xk[2], xk[3], xk[4], xk[5], shk, uk[0], uk[1]};
+        double pd9[9];
+        for (int a = 0; a < 9; ++a) {
+          const double ref = w.s(k, lw::XR + a);
+          const double dr = 1.0 / fmax(1.0, fabs(ref));
+          pd9[a] = zeta * dr * dr;
+          pgr[a] = pd9[a] * (v9[a] - ref);
+          w.s(k, lw::PG + a) = pgr[a];
+        }
+        gcost[0] = pgr[0]; gcost[1] = pgr[1]; gcost[2] = pgr[6]; gcost[3] = pgr[3]; gcost[4] = pgr[4];
+        hc[0] = pd9[0]; hc[3] = pd9[1]; hc[5] = pd9[6]; hc[6] = pd9[3]; hc[7] = pd9[4];
+        hc[8] = pd9[2]; hc[9] = pd9[5];
+        pdu[0] = pd9[7]; pdu[1] = pd9[8];
+        if (cfg.lane_con && on(m, kLane)) {
+          const double yl = ydl * ddl;
+          hc[2] += yl * sc.hC02;
+          hc[4] += yl * sc.hC12;
+          hc[5] += yl * sc.hC22;
+        }
+      } else if (mode == 0) {
         for (int a = 0; a < 6; ++a) hc[a] = df * sc.h3[a];
         hc[6] = df * sc.hvx;
         hc[7] = df * sc.hvy;
@@ -449,6 +482,10 @@ struct LaneSolver {
         double v = (mode == 0) ? -hm[a] : 0.0;
         if (a == hm_idx(1, 1)) v += hcp[6];
         if (a == hm_idx(2, 2)) v += hcp[7];
+        if (a == hm_idx(0, 0)) v += hcp[8];
+        if (a == hm_idx(3, 3)) v += hcp[9];
+        if (a == hm_idx(4, 4)) v += pdu[0];
+        if (a == hm_idx(5, 5)) v += pdu[1];
         w.s(k, lw::HSD + 6 + a) = v;
       }
       for (int a = 0; a < 5; ++a) w.s(k, lw::GC + a) = gcost[a];
@@ -460,10 +497,13 @@ struct LaneSolver {
           double v = 0.0;
           if (a == hm_idx(1, 1)) v = hc[6];
           if (a == hm_idx(2, 2)) v = hc[7];
+          if (a == hm_idx(0, 0)) v = hc[8];
+          if (a == hm_idx(3, 3)) v = hc[9];
           w.t(N, lw::T_HSD + 6 + a) = v;
         }
       }
-      if (mode == 1) {
+      if (mode == 1 && keep_scaling) {
+      } else if (mode == 1) {
         // ---- gradient-based scaling at the starting point (eval ran with df = ddl = 1) ----
         for (int a = 0; a < 5; ++a) gmax = fmax(gmax, fabs(gcost[a]));
         if (k >= 1) gmax = fmax(gmax, fabs(bd2 * (sig_prev_for_scale - sigc)));
@@ -515,17 +555,17 @@ struct LaneSolver {
         }
         gxp[0] = gcost[0] + ydl * gC[0];
         gxp[1] = gcost[1] + ydl * gC[1];
-        gxp[2] = 0.0;
+        gxp[2] = pgr[2];
         gxp[3] = gcost[3];
         gxp[4] = gcost[4];
-        gxp[5] = 0.0;
+        gxp[5] = pgr[5];
         gsp = gcost[2] + ydl * gC[2];
         for (int a = 0; a < 6; ++a) lamp[a] = lamk[a];
         yprog_p = yprog;
         ru0p = -out[9] + w.s(k, lw::RYD + kThrUb) + w.s(k, lw::RYD + kThrLb) + ydthr +
-               (on(m, kDThr0) ? w.s(k, lw::RYD + kDThr0) : 0.0);
+               (on(m, kDThr0) ? w.s(k, lw::RYD + kDThr0) : 0.0) + pgr[7];
         ru1p = -out[10] + w.s(k, lw::RYD + kStUb) + w.s(k, lw::RYD + kStLb) + ydst +
-               (on(m, kDSt0) ? w.s(k, lw::RYD + kDSt0) : 0.0);
+               (on(m, kDSt0) ? w.s(k, lw::RYD + kDSt0) : 0.0) + pgr[8];
         sigc_p = sigc;
         for (int a = 0; a < 6; ++a) {
           const double c = w.s(k, lw::CRES + a), dc = w.s(k, lw::DCS + a);
@@ -555,7 +595,7 @@ struct LaneSolver {
             sum_v += fabs(vU);
           }
           dinf = fmax(dinf, fabs(rs));
-          prinf = fmax(prinf, fabs(rd));
+          if (!resto) prinf = fmax(prinf, fabs(rd));   // restoration: the rows sit in the objective
           sum_y += fabs(yd);
           double bl, bh;
           row_bounds(r, bl, bh);
@@ -569,7 +609,7 @@ struct LaneSolver {
       shp = shk;
       up[0] = uk[0];
       up[1] = uk[1];
-      for (int a = 0; a < 8; ++a) hcp[a] = hc[a];
+      for (int a = 0; a < 10; ++a) hcp[a] = hc[a];
     }
     (void)shp;
     if (mode == 1) gmax = fmax(gmax, fabs(bd2 * sig_prev_for_scale));   // stage N-1: no successor
@@ -624,6 +664,12 @@ struct LaneSolver {
           Dr = sg + dw;
           const double rdv = (rsel == 0) ? 0.0 : w.s(k, (rsel == 1 ? lw::RRD : lw::DSOC) + r);
           er = Dr * rdv + g;
+          if (resto) {
+            // row in the objective: min over ds of wq/2 (J dx - ds + rd)^2 + Sigma/2 ds^2 + g ds
+            const double kap = wq / (wq + Dr);
+            Dr *= kap;
+            er *= kap;
+          }
         } else {
           Dr = 1.0;
           er = -((row_hasU(r) ? vU : 0.0) - (row_hasL(r) ? vL : 0.0));
@@ -675,10 +721,10 @@ struct LaneSolver {
       for (int a = 27; a < 32; ++a) hN[a] = 0.0;
       gN[0] = sgn * gc[0] + q.elane * gCn[0];
       gN[1] = sgn * gc[1] + q.elane * gCn[1];
-      gN[2] = 0.0;
+      gN[2] = resto ? w.s(N - 1, lw::PG + 2) : 0.0;
       gN[3] = sgn * gc[3];
       gN[4] = sgn * gc[4];
-      gN[5] = 0.0;
+      gN[5] = resto ? w.s(N - 1, lw::PG + 5) : 0.0;
       gN[6] = sgn * gc[2] + q.elane * gCn[2];
       for (int a = 7; a < 12; ++a) gN[a] = 0.0;
       for (int a = 0; a < 32; ++a) w.t(N, lw::T_HS + a) = hN[a];
@@ -706,8 +752,12 @@ struct LaneSolver {
         for (int a = 0; a < 3; ++a) gCp[a] = w.s(k - 1, lw::GCZ + a);
       }
       const bool wrap0 = (k == 0);
-      const double bsig = (k >= 1) ? 2.0 * p.beta_delta * df : 0.0;
+      const double bsig = (k >= 1 && !resto) ? 2.0 * p.beta_delta * df : 0.0;
       const double bq = (mode == 0) ? bsig : 0.0;
+      const double pg_yaw = (resto && k >= 1) ? w.s(k - 1, lw::PG + 2) : 0.0;
+      const double pg_r = (resto && k >= 1) ? w.s(k - 1, lw::PG + 5) : 0.0;
+      const double pg_thr = resto ? w.s(k, lw::PG + 7) : 0.0;
+      const double pg_st = resto ? w.s(k, lw::PG + 8) : 0.0;
       const double dthr = wrap0 ? 0.0 : q.Dthr;
       const double dst = wrap0 ? 0.0 : q.Dst;
       double hs[32], gs[12], A[kLinRk4], b[6];
@@ -735,15 +785,15 @@ struct LaneSolver {
       const double bg = sgn * bsig * w.s(k, lw::SIGC);
       gs[0] = sgn * gcp[0] + elane_p * gCp[0];
       gs[1] = sgn * gcp[1] + elane_p * gCp[1];
-      gs[2] = 0.0;
+      gs[2] = pg_yaw;
       gs[3] = sgn * gcp[3];
       gs[4] = sgn * gcp[4];
-      gs[5] = 0.0;
+      gs[5] = pg_r;
       gs[6] = sgn * gcp[2] + elane_p * gCp[2];
       gs[7] = wrap0 ? 0.0 : -q.ethr;
       gs[8] = (wrap0 ? 0.0 : -q.esr) - bg;
-      gs[9] = ethk;
-      gs[10] = estk + bg;
+      gs[9] = ethk + pg_thr;
+      gs[10] = estk + bg + pg_st;
       gs[11] = q.eprog;
       for (int a = 0; a < 32; ++a) w.s(k, lw::HS + a) = hs[a];
       for (int a = 0; a < 12; ++a) w.s(k, lw::GS + a) = gs[a];
@@ -1033,42 +1083,47 @@ struct LaneSolver {
           double dsr = 0.0;
           if (on(m, r)) {
             const double rdv = (rsel == 0) ? 0.0 : w.s(k, (rsel == 1 ? lw::RRD : lw::DSOC) + r);
-            dsr = row_lin(r, dcur + 7, dup, dcur[6], dshp, dcur, gC) + rdv;
-            th += fabs(w.s(k, lw::RRD + r));
+            const double jdx = row_lin(r, dcur + 7, dup, dcur[6], dshp, dcur, gC);
             const double s = w.s(k, lw::RS + r);
-            double sg = 0.0, gb = 0.0;
+            const double vL = row_hasL(r) ? w.s(k, lw::RVL + r) : 0.0;
+            const double vU = row_hasU(r) ? w.s(k, lw::RVU + r) : 0.0;
+            double sg, gb;
+            sigma_gsb(r, s, vL, vU, sg, gb);
+            dsr = jdx + rdv;
+            if (resto) {
+              const double den = wq + sg + dw;
+              dsr = (wq * (jdx + rdv) - gb) / den;
+              // directional derivative of wq/2 (d - s)^2 along (dx, ds)
+              gfd += wq * w.s(k, lw::RRD + r) * (jdx - dsr);
+            } else {
+              th += fabs(w.s(k, lw::RRD + r));
+            }
             if (row_hasL(r)) {
               const double sl = s - lo(r);
-              const double vL = w.s(k, lw::RVL + r);
               if (dsr < 0.0) a_pr = fmin(a_pr, -tau * sl / dsr);
               gsds += (-mu / sl + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * dsr;
-              const double isl = 1.0 / sl;
-              sg += vL * isl;
-              gb -= mu * isl;
-              if (!row_hasU(r)) gb += o.kappa_d * mu;
               const double dv = mu / sl - vL - vL / sl * dsr;
               if (dv < 0.0) a_du = fmin(a_du, -tau * vL / dv);
             }
             if (row_hasU(r)) {
               const double su = hi(r) - s;
-              const double vU = w.s(k, lw::RVU + r);
               if (dsr > 0.0) a_pr = fmin(a_pr, tau * su / dsr);
               gsds += (mu / su - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * dsr;
-              const double isu = 1.0 / su;
-              sg += vU * isu;
-              gb += mu * isu;
-              if (!row_hasL(r)) gb -= o.kappa_d * mu;
               const double dv = mu / su - vU + vU / su * dsr;
               if (dv < 0.0) a_du = fmin(a_du, -tau * vU / dv);
             }
-            w.s(k, lw::RDYD + r) = (sg + dw) * dsr + gb - w.s(k, lw::RYD + r);
+            w.s(k, lw::RDYD + r) = resto ? 0.0 : ((sg + dw) * dsr + gb - w.s(k, lw::RYD + r));
           }
           w.s(k, lw::RDSR + r) = dsr;
         }
         // grad f' d
-        gfd += w.s(k, lw::GC + 0) * dcur[0] + w.s(k, lw::GC + 1) * dcur[1] + w.s(k, lw::GC + 2) * dcur[6] +
-               w.s(k, lw::GC + 3) * dcur[3] + w.s(k, lw::GC + 4) * dcur[4];
-        if (k >= 1) gfd += 2.0 * p.beta_delta * df * w.s(k, lw::SIGC) * (dcur[8] - dprev[8]);
+        if (resto) {
+          for (int a = 0; a < 9; ++a) gfd += w.s(k, lw::PG + a) * dcur[a];   // (x, s_hat, u) order = step order
+        } else {
+          gfd += w.s(k, lw::GC + 0) * dcur[0] + w.s(k, lw::GC + 1) * dcur[1] + w.s(k, lw::GC + 2) * dcur[6] +
+                 w.s(k, lw::GC + 3) * dcur[3] + w.s(k, lw::GC + 4) * dcur[4];
+          if (k >= 1) gfd += 2.0 * p.beta_delta * df * w.s(k, lw::SIGC) * (dcur[8] - dprev[8]);
+        }
       }
       for (int a = 0; a < 9; ++a) dcur[a] = dprev[a];
     }
@@ -1086,7 +1141,8 @@ struct LaneSolver {
   // -------------------------------------------------------------------------
   struct Trial { double f, theta, barB; bool finite; };
 
-  MPCR_D void pass_trial(double at, Trial& t) {
+  // inner: restoration objective (rows + proximity term) and theta without the rows
+  MPCR_D void pass_trial(double at, Trial& t, bool inner, double dfu) {
     const double Ts = cfg.Ts;
     double xp[6], shp = pb.s0, up[2];
     for (int a = 0; a < 6; ++a) xp[a] = pb.x0[a];
@@ -1107,11 +1163,21 @@ struct LaneSolver {
       lane_step<MODEL, IG>(xp, tu, Ts, f);
       StageCost sc;
       stage_cost(p, pb.cx, pb.cy, tx, tsh, 0, sc);
-      double fl = sc.val;
-      if (k == N - 1) fl -= p.lambda_s * tsh;
-      if (k >= 1) {
-        const double dsg = tu[1] - up[1];
-        fl += p.beta_delta * dsg * dsg;
+      double fl = 0.0;
+      if (!inner) {
+        fl = sc.val;
+        if (k == N - 1) fl -= p.lambda_s * tsh;
+        if (k >= 1) {
+          const double dsg = tu[1] - up[1];
+          fl += p.beta_delta * dsg * dsg;
+        }
+      } else {
+        const double v9[9] = {tx[0], tx[1], tx[2], tx[3], tx[4], tx[5], tsh, tu[0], tu[1]};
+        for (int a = 0; a < 9; ++a) {
+          const double ref = w.s(k, lw::XR + a);
+          const double dr = 1.0 / fmax(1.0, fabs(ref));
+          fl += 0.5 * zeta * dr * dr * (v9[a] - ref) * (v9[a] - ref);
+        }
       }
       double thk = 0.0;
       for (int a = 0; a < 6; ++a) {
@@ -1126,7 +1192,8 @@ struct LaneSolver {
         if (on(m, r)) {
           const double sv = w.s(k, lw::RS + r) + at * w.s(k, lw::RDSR + r);
           rdv = row_value(r, tu, up, tsh, shp, sc.eC) - sv;
-          thk += fabs(rdv);
+          if (inner) fl += 0.5 * wq * rdv * rdv;
+          else thk += fabs(rdv);
           if (row_hasL(r)) {
             const double sl = sv - lo(r);
             prod *= sl;
@@ -1152,7 +1219,7 @@ struct LaneSolver {
       up[0] = tu[0];
       up[1] = tu[1];
     }
-    t.f = df * fsum;
+    t.f = dfu * fsum;
     t.theta = th;
     t.barB = bar;
     t.finite = fin;
@@ -1164,12 +1231,12 @@ struct LaneSolver {
     bool ok = true;
 #pragma unroll 1
     for (int i = 0; i < n; ++i)
-      ok = ok && ((th <= w.t(N, lw::T_FTH + i)) || (ph <= w.t(N, lw::T_FPH + i)));
+      ok = ok && ((th <= w.t(N, fbase_th + i)) || (ph <= w.t(N, fbase_ph + i)));
     return ok;
   }
   MPCR_D void filter_add(double th, double ph) {
-    w.t(N, lw::T_FTH + (filt_n & 31)) = th;
-    w.t(N, lw::T_FPH + (filt_n & 31)) = ph;
+    w.t(N, fbase_th + (filt_n & 31)) = th;
+    w.t(N, fbase_ph + (filt_n & 31)) = ph;
     filt_n++;
   }
   MPCR_D static bool cmp_le(double a, double b, double ref) {
@@ -1215,6 +1282,11 @@ struct LaneSolver {
     filt_n = 0;
     fval = 0.0;
     barB = 0.0;
+    resto = false;
+    wq = o.resto_weight;
+    zeta = 0.0;
+    fbase_th = lw::T_FTH;
+    fbase_ph = lw::T_FPH;
     Dw[0] = Dw[1] = 0.0;
     for (int r = 0; r < kNumRows; ++r) { lo_[r] = -inf; hi_[r] = inf; }
 
@@ -1229,14 +1301,117 @@ struct LaneSolver {
     Trial tp;
     tp.f = tp.theta = tp.barB = 0.0;
     tp.finite = true;
+    // restoration bookkeeping: the outer problem's scalars while the restoration phase runs
+    bool want_resto = false, reinit = false;
+    int resto_it = 0, filt_n_o = 0, acc_o = 0;
+    double mu_o = 0.0, tau_o = 0.0, df_o = 1.0, theta_max_o = 0.0, theta_min_o = 0.0, mu_floor_o = 0.0;
+    double theta_R = 0.0;
 
     while (true) {
+      if (want_resto) {
+        // ---- enter the restoration phase at the current iterate (x_R, s_R) ---------------------
+        want_resto = false;
+        theta_R = theta;
+        filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);   // IPOPT: the start point enters the filter
+        mu_o = mu; tau_o = tau; df_o = df; theta_max_o = theta_max; theta_min_o = theta_min;
+        mu_floor_o = mu_floor; filt_n_o = filt_n; acc_o = acc_count;
+        double vmax = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+          const unsigned m = rowmask(k);
+          for (int a = 0; a < 6; ++a) {
+            w.s(k, lw::XR + a) = w.s(k, lw::X + a);
+            vmax = fmax(vmax, fabs(w.s(k, lw::DCS + a) * w.s(k, lw::CRES + a)));
+            w.s(k, lw::LAM + a) = 0.0;
+          }
+          w.s(k, lw::XR + 6) = w.s(k, lw::SH);
+          w.s(k, lw::XR + 7) = w.s(k, lw::U);
+          w.s(k, lw::XR + 8) = w.s(k, lw::U + 1);
+          for (int a = 0; a < 9; ++a) w.s(k, lw::DX + a) = 0.0;
+#pragma unroll 1
+          for (int r = 0; r < kNumRows; ++r) {
+            w.s(k, lw::RDSR + r) = 0.0;
+            if (!on(m, r)) continue;
+            const double rd0 = w.s(k, lw::RRD + r);
+            vmax = fmax(vmax, fabs(rd0));
+            const double dval = rd0 + w.s(k, lw::RS + r);
+            double v = w.s(k, lw::RS + r);
+            const double l = lo(r), h = hi(r);
+            double pl, pu;
+            if (row_hasL(r) && row_hasU(r)) {
+              pl = fmin(o.bound_push * fmax(1.0, fabs(l)), o.bound_frac * (h - l));
+              pu = fmin(o.bound_push * fmax(1.0, fabs(h)), o.bound_frac * (h - l));
+            } else {
+              pl = o.bound_push * fmax(1.0, fabs(l));
+              pu = o.bound_push * fmax(1.0, fabs(h));
+            }
+            if (row_hasL(r)) v = fmax(v, l + pl);
+            if (row_hasU(r)) v = fmin(v, h - pu);
+            w.s(k, lw::RS + r) = v;
+            w.s(k, lw::RRD + r) = dval - v;
+            w.s(k, lw::RYD + r) = wq * (dval - v);
+            w.s(k, lw::RVL + r) = row_hasL(r) ? o.bound_mult_init_val : 0.0;
+            w.s(k, lw::RVU + r) = row_hasU(r) ? o.bound_mult_init_val : 0.0;
+          }
+        }
+        for (int a = 0; a < 7; ++a) y0[a] = 0.0;
+        mu = fmax(mu_o, vmax);
+        tau = fmax(o.tau_min, 1.0 - mu);
+        zeta = sqrt(mu);
+        df = 1.0;
+        mu_floor = fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0));
+        fbase_th = lw::T_FTH2;
+        fbase_ph = lw::T_FPH2;
+        filt_n = 0;
+        acc_count = 0;
+        resto = true;
+        resto_it = 0;
+        alpha = 0.0;
+        phase = kPhInit2;          // evaluate the start point with the restoration objective
+      }
       // ================= A. derivatives, convergence tests, barrier update ===============
+      if (resto && phase == kPhNewton && resto_it >= 1) {
+        // ---- leave the restoration phase?  The point must be acceptable to the ORIGINAL filter and
+        //      have reduced the original infeasibility by kappa_resto ------------------------------
+        Trial to;
+        pass_trial(0.0, to, false, df_o);
+        bool leave = to.finite && to.theta <= o.kappa_resto * theta_R && to.theta <= theta_max_o;
+        if (leave) {
+          const double ph_o = to.f + mu_o * to.barB;
+          const int n = filt_n_o < 32 ? filt_n_o : 32;
+#pragma unroll 1
+          for (int i = 0; i < n; ++i)
+            leave = leave && ((to.theta <= w.t(N, lw::T_FTH + i)) || (ph_o <= w.t(N, lw::T_FPH + i)));
+        }
+        if (leave) {
+          resto = false;
+          mu = mu_o; tau = tau_o; df = df_o; theta_max = theta_max_o; theta_min = theta_min_o;
+          mu_floor = mu_floor_o; filt_n = filt_n_o; acc_count = acc_o;
+          fbase_th = lw::T_FTH;
+          fbase_ph = lw::T_FPH;
+#pragma unroll 1
+          for (int k = 0; k < N; ++k) {
+            const unsigned m = rowmask(k);
+#pragma unroll 1
+            for (int r = 0; r < kNumRows; ++r) {
+              w.s(k, lw::RVL + r) = (on(m, r) && row_hasL(r)) ? o.bound_mult_init_val : 0.0;
+              w.s(k, lw::RVU + r) = (on(m, r) && row_hasU(r)) ? o.bound_mult_init_val : 0.0;
+            }
+          }
+          reinit = true;           // least-squares multipliers at the restored point, then resume
+          phase = kPhInit;
+        } else if (resto_it >= o.resto_max_iter) {
+          status = kRestorationNeeded;
+          break;
+        }
+      }
       if (phase == kPhInit || phase == kPhNewton) {
         Errors e;
         double gmax = 0.0, ddlmin = 1.0;
-        pass_derivs(phase == kPhInit ? 1 : 0, e, gmax, ddlmin);
-        if (phase == kPhInit) {
+        pass_derivs(phase == kPhInit ? 1 : 0, e, gmax, ddlmin, reinit);
+        if (phase == kPhInit && reinit) {
+          // scaling, bounds and mu of the outer problem stay as they are
+        } else if (phase == kPhInit) {
           if (gmax > o.nlp_scaling_max_gradient)
             df = fmax(o.nlp_scaling_max_gradient / gmax, o.nlp_scaling_min_value);
           ddl = ddlmin;
@@ -1266,12 +1441,13 @@ struct LaneSolver {
           if (!finite_d(E0)) {
             status = kInvalidNumber;
             done = true;
-          } else if (E0 <= o.tol && e.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
+          } else if (E0 <= o.tol && e.dual_inf / df <= o.dual_inf_tol && (resto || viol <= o.constr_viol_tol) &&
                      cmp0 / df <= o.compl_inf_tol) {
-            status = kSolveSucceeded;
+            // restoration: a stationary point of the infeasibility measure that the filter rejects
+            status = resto ? kRestorationNeeded : kSolveSucceeded;
             done = true;
           } else {
-            if (E0 <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
+            if (!resto && E0 <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
                 viol <= o.acceptable_constr_viol_tol && cmp0 / df <= o.acceptable_compl_inf_tol) {
               acc_count++;
               if (acc_count >= o.acceptable_iter) {
@@ -1398,7 +1574,11 @@ struct LaneSolver {
             a_du = sv_a_du;
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
-            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+            if (!(alpha >= amin && n_ls < 60)) {
+              if (o.restoration && !resto) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
           } else {
             a_soc = si.a_pr;
             a_du = si.a_du;
@@ -1406,8 +1586,12 @@ struct LaneSolver {
         }
       }
       // ================= C. trial point (single call site) =======================================
-      pass_trial((phase == kPhSoc) ? a_soc : alpha, tp);
+      pass_trial((phase == kPhSoc) ? a_soc : alpha, tp, resto, df);
       // ================= D. decisions ===========================================================
+      if (phase == kPhInit && reinit) {
+        phase = kPhInit2;          // the slacks of the restored point are kept
+        continue;
+      }
       if (phase == kPhInit) {
         // slacks pushed into their (relaxed) bounds; RTRD holds the row values (s was 0)
 #pragma unroll 1
@@ -1444,8 +1628,11 @@ struct LaneSolver {
         fval = tp.f;
         barB = tp.barB;
         cur_finite = tp.finite;
-        theta_max = o.theta_max_fact * fmax(1.0, tp.theta);
-        theta_min = o.theta_min_fact * fmax(1.0, tp.theta);
+        if (!reinit) {
+          theta_max = o.theta_max_fact * fmax(1.0, tp.theta);
+          theta_min = o.theta_min_fact * fmax(1.0, tp.theta);
+        }
+        reinit = false;
         phase = kPhNewton;
         continue;
       }
@@ -1475,7 +1662,11 @@ struct LaneSolver {
             a_du = sv_a_du;
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
-            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+            if (!(alpha >= amin && n_ls < 60)) {
+              if (o.restoration && !resto) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
           } else {
             th_old = tp.theta;
 #pragma unroll 1
@@ -1508,7 +1699,11 @@ struct LaneSolver {
         }
         alpha *= o.alpha_red_factor;
         phase = kPhBacktrack;
-        if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+        if (!(alpha >= amin && n_ls < 60)) {
+              if (o.restoration && !resto) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
         continue;
       }
       // ================= E. accept the trial point ===============================================
@@ -1551,6 +1746,7 @@ struct LaneSolver {
           }
           w.s(k, lw::RS + r) = snew;
           w.s(k, lw::RRD + r) = w.s(k, lw::RTRD + r);
+          if (resto) w.s(k, lw::RYD + r) = wq * w.s(k, lw::RTRD + r);
         }
       }
       for (int a = 0; a < 7; ++a) y0[a] += astep * (newy0[a] - y0[a]);
@@ -1559,6 +1755,7 @@ struct LaneSolver {
       cur_finite = tp.finite;
       last_alpha = astep;
       it++;
+      if (resto) resto_it++;
       phase = kPhNewton;
     }
 

@@ -46,6 +46,10 @@ struct IpmOptions {
   double kappa_soc;
   double delta_w_init, delta_w_min, delta_w_max;
   double kappa_w_minus, kappa_w_plus, kappa_w_plus_first;
+  // feasibility restoration (quadratic-penalty variant): 0 = off (status -2 instead)
+  int restoration;
+  int resto_max_iter;
+  double resto_weight, kappa_resto;
 };
 
 struct Config {

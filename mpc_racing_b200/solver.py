@@ -51,7 +51,7 @@ class BatchedMPC:
                  runtime_params: Optional[RuntimeControllerParameters] = None,
                  wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
                  tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False,
-                 solve_kernel=0, integrator="euler"):
+                 solve_kernel=0, integrator="euler", restoration=False):
         self.lib = _capi.load_library()
         fp = fixed_params or FixedControllerParameters()
         rp = runtime_params or RuntimeControllerParameters()
@@ -80,6 +80,7 @@ class BatchedMPC:
         cfg.solve_kernel = int({"auto": 0, "warp": 1, "lanes": 2}.get(solve_kernel, solve_kernel))
         # "euler" = the reference's discretisation; "rk4" = extension, solved by the lane kernel
         cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
+        cfg.restoration = int(bool(restoration))     # feasibility restoration (lane kernel), off = reference-free status -2
         self.cfg = cfg
         self.N = cfg.N
         self.on_device = bool(on_device)

@@ -229,3 +229,30 @@ def test_rk4_integrator_on_gpu(cfg2):
         ref = oracle_solve(cfg2['x0'][b], cfg2['u_prev'][b], cfg2['s0'][b], cfg2['cx'][b], cfg2['cy'][b],
                            integrator='rk4')
         assert_parity(res, j, ref)
+
+
+def test_restoration_rescue_pass_on_gpu():
+    """mpcr_config.restoration on the GPU: the warp kernel's status -2 problems are re-solved by the
+    lane kernel with the feasibility-restoration phase (rescue pass); with solve_kernel = lanes the
+    phase runs in place.  Config 3 (lane rows): 25 of 512 problems need it."""
+    import os
+    from mpc_racing_b200.solver import BatchedMPC
+    d = load_fixture("cfg3_t1_triple_512.npz")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg3_t1_triple_512_oracle.npz"))
+    args = (d['x0'], d['u_prev'], d['s0'], d['cx'], d['cy'])
+    plain = BatchedMPC(N=30, Ts=0.05, lane_constraint=True).solve(*args, max_err=d['max_err'])
+    resc = BatchedMPC(N=30, Ts=0.05, lane_constraint=True, restoration=True).solve(*args, max_err=d['max_err'])
+    lanes = BatchedMPC(N=30, Ts=0.05, lane_constraint=True, restoration=True, solve_kernel="lanes").solve(
+        *args, max_err=d['max_err'])
+    assert (plain.status == -2).sum() >= 20
+    assert (resc.status >= 0).mean() >= 0.995 and (lanes.status >= 0).mean() >= 0.995
+    untouched = plain.status >= 0
+    assert np.array_equal(resc.U[untouched], plain.U[untouched])          # the rescue pass only touches failures
+    both = (resc.status >= 0) & (lanes.status >= 0)
+    rel = np.abs(resc.obj - lanes.obj)[both] / np.abs(lanes.obj[both])
+    assert (rel <= 1e-6).mean() >= 0.99
+    # a rescued problem against the oracle's restoration study and the independent optimum
+    b = 478
+    assert plain.status[b] == -2 and resc.status[b] == 0
+    assert abs(resc.obj[b] - (-112828.3055199883)) <= 1e-6 * 112828.3
+    assert g['status'][b] == -2

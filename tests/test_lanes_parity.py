@@ -86,3 +86,35 @@ def test_rk4_integrator_nlp(cfg2):
     fe = V.f_dynamic(X[:, :-1].T, U.T, 0.05).T
     assert np.abs(X[:, 1:] - f4).max() <= 1e-4
     assert np.abs(X[:, 1:] - fe).max() > 1e-3
+
+
+def test_restoration_phase_rescues_lane_row_failures():
+    """mpcr_config.restoration: when the filter line search fails the lane solver minimises
+    wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 over the same (x, s) until the original filter
+    accepts a point with theta reduced by kappa_resto, then resumes.  The oracle's
+    restoration study (oracle/restoration.py, RestoQuadNLP) reaches the same optima."""
+    d = load_fixture("cfg3_t1_triple_512.npz")
+    idx = [28, 478, 499]                     # status -2 without restoration (tests/golden/*_oracle.npz)
+    a = lambda k: d[k][idx]
+    plain = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), max_err=a('max_err'), lane_constraint=1,
+                      lanes=True)
+    assert (plain['status'] == -2).all()
+    out = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), max_err=a('max_err'), lane_constraint=1,
+                    lanes=True, restoration=1)
+    assert (out['status'] == 0).all()
+    for j, b in enumerate(idx):
+        ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], lane=True,
+                           max_error=float(d['max_err'][b]), options=dict(restoration='quad'))
+        assert ref['status'] == 0
+        assert abs(out['obj'][j] - ref['obj']) <= 1e-6 * abs(ref['obj']), (b, out['obj'][j], ref['obj'])
+        dU = np.abs(out['U'][j] - ref['U'])
+        dU[0, -1] = 0.0
+        assert dU.max() <= 2e-3, (b, dU.max())      # different restoration paths, same optimum
+    assert abs(out['obj'][1] - (-112828.3055199883)) <= 1e-6 * 112828.3     # scipy trust-constr optimum of #478
+    # problems that do not need it are untouched by the option
+    cfg2 = load_fixture("cfg2_shanghai_4096.npz")
+    i = [0, 1, 2]
+    r0 = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], lanes=True)
+    r1 = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], lanes=True,
+                   restoration=1)
+    assert np.array_equal(r0['U'], r1['U']) and np.array_equal(r0['iters'], r1['iters'])
