@@ -93,7 +93,8 @@ typedef struct mpcr_config {
                               * solved by the lane kernel) */
   int32_t restoration;       /* 1: when the filter line search fails, run the feasibility-restoration phase
                               * (IPOPT would; quadratic-penalty variant) instead of returning
-                              * MPCR_RESTORATION_FAILED.  Implemented by the lane kernel. 0 = off (default) */
+                              * MPCR_RESTORATION_FAILED.  Selects the kernel build that contains the phase
+                              * (~20 % slower per solve).  0 = off (default) */
   int32_t reserved_;
 } mpcr_config;
 

@@ -28,7 +28,7 @@ namespace mpcr {
 #ifndef MPCR_MIN_BLOCKS
 #define MPCR_MIN_BLOCKS 1
 #endif
-template <int MODEL, bool STAGE_GLOBAL>
+template <int MODEL, bool STAGE_GLOBAL, bool RESTO>
 __global__ void __launch_bounds__(32, MPCR_MIN_BLOCKS)
 solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
              int trace_rows, int* __restrict__ counter, double* __restrict__ slabs) {
@@ -40,22 +40,25 @@ solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOu
     if (lane == 0) b = atomicAdd(counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= B) break;
-    solve_problem<MODEL, STAGE_GLOBAL>(cfg, in, out, b, trace_rows, smem, stage);
+    solve_problem<MODEL, STAGE_GLOBAL, RESTO>(cfg, in, out, b, trace_rows, smem, stage);
     __syncwarp();
   }
 }
 
 typedef void (*SolveKernelFn)(const Config, const BatchIn, const BatchOut, int, int, int*, double*);
 
-static SolveKernelFn pick_kernel(int model, bool stage_global) {
-  if (stage_global) {
-    if (model == kDynamic) return solve_kernel<kDynamic, true>;
-    if (model == kKinematic) return solve_kernel<kKinematic, true>;
-    return solve_kernel<kBlended, true>;
-  }
-  if (model == kDynamic) return solve_kernel<kDynamic, false>;
-  if (model == kKinematic) return solve_kernel<kKinematic, false>;
-  return solve_kernel<kBlended, false>;
+template <bool SG, bool RS>
+static SolveKernelFn pick_kernel_m(int model) {
+  if (model == kDynamic) return solve_kernel<kDynamic, SG, RS>;
+  if (model == kKinematic) return solve_kernel<kKinematic, SG, RS>;
+  return solve_kernel<kBlended, SG, RS>;
+}
+
+// restoration: the kernel build that contains the feasibility-restoration phase (the plain build
+// carries none of its code or registers)
+static SolveKernelFn pick_kernel(int model, bool stage_global, bool restoration) {
+  if (stage_global) return restoration ? pick_kernel_m<true, true>(model) : pick_kernel_m<true, false>(model);
+  return restoration ? pick_kernel_m<false, true>(model) : pick_kernel_m<false, false>(model);
 }
 
 // Throughput kernel: one problem per LANE (mpcr_ipm_lanes.cuh).  Block = one warp; warp w owns
@@ -72,36 +75,6 @@ lane_solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const Ba
 }
 
 typedef void (*LaneKernelFn)(const Config, const BatchIn, const BatchOut, int, int, double*, int);
-
-// Rescue pass (mpcr_config.restoration with the warp kernel): the problems the warp kernel left
-// with status MPCR_RESTORATION_FAILED are collected and solved again by the lane solver, which has
-// the feasibility-restoration phase (it follows the same iteration path up to the failure).
-__global__ void __launch_bounds__(256) collect_failed_kernel(const int32_t* __restrict__ status, int B,
-                                                             int* __restrict__ list, int* __restrict__ count) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B && status[b] == kRestorationNeeded) list[atomicAdd(count, 1)] = b;
-}
-
-template <int MODEL, int IG>
-__global__ void __launch_bounds__(32, 1)
-lane_rescue_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out,
-                   const int* __restrict__ list, const int* __restrict__ count, int trace_rows,
-                   double* __restrict__ ws, int ws_doubles) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 32 + lane;
-  if (i >= *count) return;
-  double* w = ws + (size_t)blockIdx.x * ws_doubles * 32 + lane;
-  lane_solve_problem<MODEL, IG>(cfg, in, out, list[i], trace_rows, w);
-}
-
-typedef void (*RescueKernelFn)(const Config, const BatchIn, const BatchOut, const int*, const int*, int,
-                               double*, int);
-
-static RescueKernelFn pick_rescue_kernel(int model) {
-  if (model == kDynamic) return lane_rescue_kernel<kDynamic, 0>;
-  if (model == kKinematic) return lane_rescue_kernel<kKinematic, 0>;
-  return lane_rescue_kernel<kBlended, 0>;
-}
 
 static LaneKernelFn pick_lane_kernel(int model, int integrator) {
   if (integrator == MPCR_INTEGRATOR_RK4) {
@@ -143,9 +116,6 @@ struct mpcr_handle {
   bool stage_global = false;
   SolveKernelFn kernel = nullptr;
   LaneKernelFn lane_kernel = nullptr;
-  RescueKernelFn rescue_kernel = nullptr;
-  int* d_rescue = nullptr;               // [0] = count, [1..] = indices of the problems to rescue
-  int rescue_cap = 0;
   int kernel_sel = MPCR_KERNEL_AUTO;     // config / MPCR_KERNEL env
   // AUTO: batches at least this large use the lane kernel.  Measured on B200 (profiles/r1e_*):
   // at B = 16384 the lane kernel is 4x SLOWER than the warp kernel (16k threads cannot hide the
@@ -202,10 +172,8 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
     const char* e = getenv("MPCR_STAGE_GLOBAL");
     h->stage_global = e ? (atoi(e) != 0) : false;
   }
-  h->kernel = pick_kernel(h->cfg.model, h->stage_global);
+  h->kernel = pick_kernel(h->cfg.model, h->stage_global, h->cfg.o.restoration != 0);
   h->lane_kernel = pick_lane_kernel(h->cfg.model, h->cfg.integrator);
-  h->rescue_kernel = pick_rescue_kernel(h->cfg.model);
-  CK(cudaFuncSetAttribute(h->rescue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   h->kernel_sel = cfg->solve_kernel;
   {
     const char* e = getenv("MPCR_KERNEL");
@@ -249,7 +217,6 @@ extern "C" int mpcr_destroy(mpcr_handle* h) {
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_slabs) cudaFree(h->d_slabs);
   if (h->d_lane_ws) cudaFree(h->d_lane_ws);
-  if (h->d_rescue) cudaFree(h->d_rescue);
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->d_ibuf) cudaFree(h->d_ibuf);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -286,7 +253,7 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
                      (h->kernel_sel == MPCR_KERNEL_AUTO && B >= h->lanes_min_batch);
   const size_t warps = ((size_t)B + 31) / 32;
   const int wsd = lane_ws_doubles(h->cfg.N);
-  if (lanes || h->cfg.o.restoration) {
+  if (lanes) {
     if (warps > h->lane_ws_warps) {
       if (h->d_lane_ws) cudaFree(h->d_lane_ws);
       h->d_lane_ws = nullptr;
@@ -328,21 +295,6 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
   CK(cudaEventRecord(h->ev0, st));
   h->kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, h->d_slabs);
   CK(cudaGetLastError());
-  if (h->cfg.o.restoration) {
-    if (B > h->rescue_cap) {
-      if (h->d_rescue) cudaFree(h->d_rescue);
-      h->d_rescue = nullptr;
-      h->rescue_cap = 0;
-      CK(cudaMalloc(&h->d_rescue, ((size_t)B + 1) * sizeof(int)));
-      h->rescue_cap = B;
-    }
-    CK(cudaMemsetAsync(h->d_rescue, 0, sizeof(int), st));
-    collect_failed_kernel<<<(B + 255) / 256, 256, 0, st>>>(out.status, B, h->d_rescue + 1, h->d_rescue);
-    CK(cudaGetLastError());
-    h->rescue_kernel<<<(unsigned)warps, 32, 0, st>>>(h->cfg, in, out, h->d_rescue + 1, h->d_rescue, trace_rows,
-                                                     h->d_lane_ws, wsd);
-    CK(cudaGetLastError());
-  }
   CK(cudaEventRecord(h->ev1, st));
   h->timed = true;
   return MPCR_OK;

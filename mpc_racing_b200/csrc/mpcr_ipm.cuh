@@ -208,7 +208,8 @@ struct SolveOut {        // pointers already offset to this problem
 
 // solver phases: every heavy routine has exactly ONE call site inside the phase loop
 // (keeps the kernel's instruction footprint inside the SM instruction cache)
-enum Phase : int { kPhInit = 0, kPhInit2 = 1, kPhNewton = 2, kPhBacktrack = 3, kPhSoc = 4 };
+enum Phase : int { kPhInit = 0, kPhInit2 = 1, kPhNewton = 2, kPhBacktrack = 3, kPhSoc = 4,
+                   kPhRestoCheck = 5 };   // restoration: evaluate the ORIGINAL merit at the new point
 
 // ---------------------------------------------------------------------------
 // The solver.  All members are per-lane unless noted "uniform".
@@ -220,9 +221,15 @@ struct RowState {
   double s[kNumRows], yd[kNumRows], vL[kNumRows], vU[kNumRows];
   double rd[kNumRows];      // d_r(x) - s_r at the current iterate
   double dsr[kNumRows];     // slack step of the current direction
+  // feasibility restoration: reference point (x, s_hat, u) of this lane's stage and the gradient
+  // of the proximity term over the same 9 variables
+  double xr[9], pg[9];
+  double osave[12];         // the outer problem's scalars while the restoration phase runs
 };
 
-template <int MODEL, bool SG = false>
+// RESTO: compile the feasibility-restoration phase in (mpcr_config.restoration); the RESTO = false
+// instantiation is the plain solver without any of its code or registers.
+template <int MODEL, bool SG = false, bool RESTO = false>
 struct WarpSolver {
   const Config& cfg;
   const Params& p;        // per-problem copy (GA sweeps override the runtime parameters)
@@ -249,6 +256,11 @@ struct WarpSolver {
   // filter: one entry per lane
   double filt_th, filt_ph;
   int filt_n;
+  // feasibility restoration (quadratic-penalty variant, same text as LaneSolver): while `in_resto()` is set
+  // the objective is wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 and the rows' multipliers are wq (d - s)
+  bool resto_;
+  double wq, zeta;
+  MPCR_D bool in_resto() const { return RESTO && resto_; }
   // packed slots of the stage-Hessian entries (r, lane), r = 0..11, one byte each (registers,
   // no runtime-indexed local array): rows 0-7 in colslot_lo, rows 8-11 in colslot_hi
   unsigned long long colslot_lo;
@@ -345,7 +357,9 @@ struct WarpSolver {
   };
 
   // slacks of the point are s + at * dsr (not stored)
-  MPCR_D void eval_point(Point& t, double* trd /* [kNumRows] out: d_r - s_r */, double at) const {
+  // inner: restoration objective and theta without the rows; dfu: objective scaling to apply
+  MPCR_D void eval_point(Point& t, double* trd /* [kNumRows] out: d_r - s_r */, double at, bool inner,
+                         double dfu) const {
     double xp[6], shp, up[2];
     gather_prev(t.x, t.sh, t.u, xp, shp, up);
     double f[6];
@@ -357,11 +371,21 @@ struct WarpSolver {
     bool fin = true;
     for (int k = 0; k < 6; ++k) t.c[k] = 0.0;
     if (act) {
-      fl = sc.val;
-      if (lane == N - 1) fl -= p.lambda_s * t.sh;
-      if (lane >= 1) {
-        double dsg = t.u[1] - up[1];
-        fl += p.beta_delta * dsg * dsg;
+      if (!inner) {
+        fl = sc.val;
+        if (lane == N - 1) fl -= p.lambda_s * t.sh;
+        if (lane >= 1) {
+          double dsg = t.u[1] - up[1];
+          fl += p.beta_delta * dsg * dsg;
+        }
+      } else {
+        const double v9[9] = {t.x[0], t.x[1], t.x[2], t.x[3], t.x[4], t.x[5], t.sh, t.u[0], t.u[1]};
+#pragma unroll 1
+        for (int a = 0; a < 9; ++a) {
+          const double ref = R.xr[a];
+          const double dr = 1.0 / fmax(1.0, fabs(ref));
+          fl += 0.5 * zeta * dr * dr * (v9[a] - ref) * (v9[a] - ref);
+        }
       }
       for (int k = 0; k < 6; ++k) {
         t.c[k] = t.x[k] - f[k];
@@ -374,7 +398,8 @@ struct WarpSolver {
       if (on(r)) {
         const double sv = R.s[r] + at * R.dsr[r];
         rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
-        th += fabs(rdv);
+        if (inner) fl += 0.5 * wq * rdv * rdv;
+        else th += fabs(rdv);
         if (row_hasL(r)) {
           const double sl = sv - lo(r);
           prod *= sl;
@@ -393,7 +418,7 @@ struct WarpSolver {
     double bar = act ? (-log_d(prod) + o.kappa_d * lin) : 0.0;
     fin = fin && finite_d(fl) && finite_d(th) && finite_d(bar);
     t.finite = warp_all(fin);
-    t.f = df * warp_sum(fl);
+    t.f = dfu * warp_sum(fl);
     t.theta = warp_sum(th);
     t.barB = warp_sum(bar);
   }
@@ -423,11 +448,33 @@ struct WarpSolver {
     gcost[3] = df * sc.gvx;
     gcost[4] = df * sc.gvy;
     for (int k = 0; k < 3; ++k) gC[k] = ddl * sc.gC[k];
-    sigc_prev = (lane >= 1 && act) ? (u[1] - up[1]) : 0.0;
+    sigc_prev = (lane >= 1 && act && !in_resto()) ? (u[1] - up[1]) : 0.0;
     // cost Hessian of state lane+1 -> owner of stage lane+1 (shuffle up) / terminal slot
     double hc[8];
     for (int k = 0; k < 8; ++k) hc[k] = 0.0;
-    if (mode == 0 && act) {
+    double hyr[2] = {0.0, 0.0}, pdu[2] = {0.0, 0.0};   // restoration: (yaw, r) of state lane+1, (thr, st) of this stage
+    if (in_resto()) {
+      // proximity term zeta/2 |D_R (v - v_R)|^2 over (x_{k+1}, s_{k+1}, u_k) replaces the cost
+      const double v9[9] = {x[0], x[1], x[2], x[3], x[4], x[5], sh, u[0], u[1]};
+      double pd9[9];
+#pragma unroll 1
+      for (int a = 0; a < 9; ++a) {
+        const double ref = R.xr[a];
+        const double dr = 1.0 / fmax(1.0, fabs(ref));
+        pd9[a] = act ? zeta * dr * dr : 0.0;
+        R.pg[a] = pd9[a] * (v9[a] - ref);
+      }
+      gcost[0] = R.pg[0]; gcost[1] = R.pg[1]; gcost[2] = R.pg[6]; gcost[3] = R.pg[3]; gcost[4] = R.pg[4];
+      hc[0] = pd9[0]; hc[3] = pd9[1]; hc[5] = pd9[6]; hc[6] = pd9[3]; hc[7] = pd9[4];
+      hyr[0] = pd9[2]; hyr[1] = pd9[5];
+      pdu[0] = pd9[7]; pdu[1] = pd9[8];
+      if (act && cfg.lane_con && on(kLane)) {
+        double yl = R.yd[kLane] * ddl;
+        hc[2] += yl * sc.hC02;
+        hc[4] += yl * sc.hC12;
+        hc[5] += yl * sc.hC22;
+      }
+    } else if (mode == 0 && act) {
       for (int k = 0; k < 6; ++k) hc[k] = df * sc.h3[k];
       hc[6] = df * sc.hvx;
       hc[7] = df * sc.hvy;
@@ -443,6 +490,13 @@ struct WarpSolver {
       double t = shfl(hc[k], prev_lane());
       hcp[k] = (lane == 0) ? 0.0 : t;
     }
+    double hyrp[2] = {0.0, 0.0};
+    if (in_resto()) {
+      for (int k = 0; k < 2; ++k) {
+        double t = shfl(hyr[k], prev_lane());
+        hyrp[k] = (lane == 0) ? 0.0 : t;
+      }
+    }
     if (act) {
       double* st = ws.st(lane);
       for (int k = 0; k < 3; ++k) { st[kOffA + k] = lin.aX[k]; st[kOffA + 3 + k] = lin.aY[k]; }
@@ -457,6 +511,12 @@ struct WarpSolver {
       for (int k = 0; k < kHmDoubles; ++k) hs[6 + k] = (mode == 0) ? -hm[k] : 0.0;
       hs[6 + hm_idx(1, 1)] += hcp[6];
       hs[6 + hm_idx(2, 2)] += hcp[7];
+      if (in_resto()) {
+        hs[6 + hm_idx(0, 0)] += hyrp[0];
+        hs[6 + hm_idx(3, 3)] += hyrp[1];
+        hs[6 + hm_idx(4, 4)] += pdu[0];
+        hs[6 + hm_idx(5, 5)] += pdu[1];
+      }
       st[kOffBase0] = hs[6 + hm_idx(4, 4)];
       st[kOffBase1] = hs[6 + hm_idx(5, 5)];
       if (lane == N - 1) {
@@ -466,6 +526,8 @@ struct WarpSolver {
         for (int k = 0; k < kHmDoubles; ++k) hN[6 + k] = 0.0;
         hN[6 + hm_idx(1, 1)] = hc[6];
         hN[6 + hm_idx(2, 2)] = hc[7];
+        hN[6 + hm_idx(0, 0)] = hyr[0];
+        hN[6 + hm_idx(3, 3)] = hyr[1];
         for (int k = 27; k < 32; ++k) hN[k] = 0.0;
       }
     }
@@ -513,6 +575,12 @@ struct WarpSolver {
           sigma_gsb(r, sg, g);
           Dr = sg + dw;
           er = Dr * (rdv ? rdv[r] : 0.0) + g;
+          if (in_resto()) {
+            // row in the objective: min over ds of wq/2 (J dx - ds + rd)^2 + Sigma/2 ds^2 + g ds
+            const double kap = wq / (wq + Dr);
+            Dr *= kap;
+            er *= kap;
+          }
         } else {
           Dr = 1.0;
           er = -((row_hasU(r) ? R.vU[r] : 0.0) - (row_hasL(r) ? R.vL[r] : 0.0));
@@ -544,9 +612,19 @@ struct WarpSolver {
       double t = shfl(gC[k], prev_lane());
       gCp[k] = (lane == 0) ? 0.0 : t;
     }
+    // restoration: proximity gradient over (yaw, r) of state `lane` (previous lane) and over this
+    // stage's inputs
+    double pgy = 0.0, pgr = 0.0, pgt = 0.0, pgs = 0.0;
+    if (in_resto()) {
+      const double t0 = shfl(R.pg[2], prev_lane()), t1 = shfl(R.pg[5], prev_lane());
+      pgy = (lane == 0) ? 0.0 : t0;
+      pgr = (lane == 0) ? 0.0 : t1;
+      pgt = R.pg[7];
+      pgs = R.pg[8];
+    }
     if (!act) return;
     // steer-rate cost beta (sigma_k - sigma_{k-1})^2, k = 1..N-1 (control/MPC.py:97)
-    const double bsig = (lane >= 1) ? 2.0 * p.beta_delta * df : 0.0;
+    const double bsig = (lane >= 1 && !in_resto()) ? 2.0 * p.beta_delta * df : 0.0;
     const double sgn = (mode == 0) ? 1.0 : -1.0;   // LSQ uses the negated gradient
     const double bq = (mode == 0) ? bsig : 0.0;
     double* st = ws.st(lane);
@@ -577,15 +655,15 @@ struct WarpSolver {
     const double bg = sgn * bsig * sigc_prev;
     gs[0] = sgn * gcp[0] + elane_p * gCp[0];
     gs[1] = sgn * gcp[1] + elane_p * gCp[1];
-    gs[2] = 0.0;
+    gs[2] = pgy;
     gs[3] = sgn * gcp[3];
     gs[4] = sgn * gcp[4];
-    gs[5] = 0.0;
+    gs[5] = pgr;
     gs[6] = sgn * gcp[2] + elane_p * gCp[2];
     gs[7] = wrap0 ? 0.0 : -ethr;
     gs[8] = (wrap0 ? 0.0 : -esr) - bg;
-    gs[9] = ethk;
-    gs[10] = estk + bg;
+    gs[9] = ethk + pgt;
+    gs[10] = estk + bg + pgs;
     gs[11] = eprog;
     for (int k = 0; k < 6; ++k) st[kOffB + k] = cv ? -cv[k] : 0.0;
     if (lane == N - 1) {
@@ -594,10 +672,10 @@ struct WarpSolver {
       const double* bN = ws.st(N) + kOffK;
       gN[0] = sgn * gcost[0] + elane * gC[0];
       gN[1] = sgn * gcost[1] + elane * gC[1];
-      gN[2] = 0.0;
+      gN[2] = in_resto() ? R.pg[2] : 0.0;
       gN[3] = sgn * gcost[3];
       gN[4] = sgn * gcost[4];
-      gN[5] = 0.0;
+      gN[5] = in_resto() ? R.pg[5] : 0.0;
       gN[6] = sgn * gcost[2] + elane * gC[2];
       for (int k = 7; k < 12; ++k) gN[k] = 0.0;
       hN[0] = bN[0] + Dlane * gC[0] * gC[0];
@@ -919,8 +997,8 @@ struct WarpSolver {
       txn[a] = last ? 0.0 : t;
     }
     const double ydl = on(kLane) ? R.yd[kLane] : 0.0;
-    const double gx[6] = {gcost[0] + ydl * gC[0], gcost[1] + ydl * gC[1], 0.0, gcost[3],
-                          gcost[4], 0.0};
+    const double gx[6] = {gcost[0] + ydl * gC[0], gcost[1] + ydl * gC[1], in_resto() ? R.pg[2] : 0.0, gcost[3],
+                          gcost[4], in_resto() ? R.pg[5] : 0.0};
     const double yprog_n_raw = shfl(R.yd[kProg], next_lane());
     const double yprog_n = last ? 0.0 : yprog_n_raw;
     const double ydthr_n = shfl(on(kDThr) ? R.yd[kDThr] : 0.0, next_lane());
@@ -933,9 +1011,9 @@ struct WarpSolver {
       for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(gx[a] + lam[a] - txn[a]));
       dinf = fmax(dinf, fabs(gcost[2] + ydl * gC[2] + R.yd[kProg] - yprog_n));
       double ru0 = -out[9] + R.yd[kThrUb] + R.yd[kThrLb] + (on(kDThr) ? R.yd[kDThr] : 0.0) - ydthr_n +
-                   (on(kDThr0) ? R.yd[kDThr0] : 0.0);
+                   (on(kDThr0) ? R.yd[kDThr0] : 0.0) + (in_resto() ? R.pg[7] : 0.0);
       double ru1 = -out[10] + R.yd[kStUb] + R.yd[kStLb] + (on(kDSt) ? R.yd[kDSt] : 0.0) - ydst_n +
-                   (on(kDSt0) ? R.yd[kDSt0] : 0.0) +
+                   (on(kDSt0) ? R.yd[kDSt0] : 0.0) + (in_resto() ? R.pg[8] : 0.0) +
                    2.0 * p.beta_delta * df * (sigc_prev - sig_n);
       dinf = fmax(dinf, fmax(fabs(ru0), fabs(ru1)));
       if (lane == 0) {
@@ -968,7 +1046,7 @@ struct WarpSolver {
         sum_v += fabs(R.vU[r]);
       }
       dinf = fmax(dinf, fabs(rs));
-      prinf = fmax(prinf, fabs(R.rd[r]));
+      if (!in_resto()) prinf = fmax(prinf, fabs(R.rd[r]));   // restoration: the rows sit in the objective
       sum_y += fabs(R.yd[r]);
       double bl, bh;
       row_bounds(r, bl, bh);
@@ -992,9 +1070,10 @@ struct WarpSolver {
   }
 
   // filter --------------------------------------------------------------------
-  MPCR_D bool filter_ok(double th, double ph) const {
-    int n = filt_n < 32 ? filt_n : 32;
-    bool ok = (lane >= n) || (th <= filt_th) || (ph <= filt_ph);
+  MPCR_D bool filter_ok(double th, double ph) const { return filter_ok_in(th, ph, filt_th, filt_ph, filt_n); }
+  MPCR_D bool filter_ok_in(double th, double ph, double fth, double fph, int fn) const {
+    int n = fn < 32 ? fn : 32;
+    bool ok = (lane >= n) || (th <= fth) || (ph <= fph);
     return warp_all(ok);
   }
   MPCR_D void filter_add(double th, double ph) {
@@ -1007,7 +1086,7 @@ struct WarpSolver {
 
   // slack steps ds_r = J_r dx + rdv_r (into dsr) and the fraction-to-the-boundary step; the same
   // pass accumulates this lane's share of grad_s(phi)' ds and of theta = |c|_1 + |d - s|_1
-  MPCR_D double slack_steps(const double* rdv, double& gs_ds, double& th_loc) {
+  MPCR_D double slack_steps(const double* rdv, double dwu, double& gs_ds, double& th_loc) {
     double dup[2], dshp;
     dup[0] = shfl(du[0], prev_lane());
     dup[1] = shfl(du[1], prev_lane());
@@ -1020,8 +1099,17 @@ struct WarpSolver {
     for (int r = 0; r < kNumRows; ++r) {
       double d = 0.0;
       if (on(r)) {
-        d = row_lin(r, du, dup, dsh, dshp, dx) + (rdv ? rdv[r] : 0.0);
-        th += fabs(R.rd[r]);
+        const double jdx = row_lin(r, du, dup, dsh, dshp, dx);
+        d = jdx + (rdv ? rdv[r] : 0.0);
+        if (in_resto()) {
+          // slack step of a row that sits in the objective, and its share of grad(f_R)' d
+          double sg, gb;
+          sigma_gsb(r, sg, gb);
+          d = (wq * d - gb) / (wq + sg + dwu);
+          g += wq * R.rd[r] * (jdx - d);
+        } else {
+          th += fabs(R.rd[r]);
+        }
         if (row_hasL(r)) {
           const double sl = R.s[r] - lo(r);
           if (d < 0.0) a = fmin(a, -tau * sl / d);
@@ -1094,6 +1182,9 @@ struct WarpSolver {
     filt_ph = 0.0;
     fval = 0.0;
     barB = 0.0;
+    resto_ = false;
+    wq = o.resto_weight;
+    zeta = 0.0;
     {
       int nr = 0, nb = 0;
 #pragma unroll 1
@@ -1123,12 +1214,74 @@ struct WarpSolver {
     for (int a = 0; a < 7; ++a) sv_y0[a] = 0.0;
     Point tp;
     double tp_rd[kNumRows];
+    // restoration bookkeeping (the outer problem's scalars are parked in R.osave)
+    bool want_resto = false, reinit = false;
+    int resto_it = 0;
+    double theta_R = 0.0;
 
     while (true) {
+      if (RESTO && want_resto) {
+        // ---- enter the restoration phase at the current iterate (x_R, s_R) ---------------------
+        want_resto = false;
+        theta_R = theta;
+        filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);   // the start point enters the filter
+        R.osave[0] = mu; R.osave[1] = tau; R.osave[2] = df; R.osave[3] = theta_max; R.osave[4] = theta_min;
+        R.osave[5] = mu_floor; R.osave[6] = filt_th; R.osave[7] = filt_ph; R.osave[8] = (double)filt_n;
+        R.osave[9] = (double)acc_count;
+        double vmax = 0.0;
+        for (int a = 0; a < 6; ++a) {
+          R.xr[a] = x[a];
+          if (act) vmax = fmax(vmax, fabs(dcs[a] * cres[a]));
+          lam[a] = 0.0;
+          dx[a] = 0.0;
+        }
+        R.xr[6] = sh; R.xr[7] = u[0]; R.xr[8] = u[1];
+        dsh = 0.0;
+        du[0] = du[1] = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < kNumRows; ++r) {
+          R.dsr[r] = 0.0;
+          if (!on(r)) continue;
+          const double rd0 = R.rd[r];
+          vmax = fmax(vmax, fabs(rd0));
+          const double dval = rd0 + R.s[r];
+          double v = R.s[r];
+          const double l = lo(r), h = hi(r);
+          double pl, pu;
+          if (row_hasL(r) && row_hasU(r)) {
+            pl = fmin(o.bound_push * fmax(1.0, fabs(l)), o.bound_frac * (h - l));
+            pu = fmin(o.bound_push * fmax(1.0, fabs(h)), o.bound_frac * (h - l));
+          } else {
+            pl = o.bound_push * fmax(1.0, fabs(l));
+            pu = o.bound_push * fmax(1.0, fabs(h));
+          }
+          if (row_hasL(r)) v = fmax(v, l + pl);
+          if (row_hasU(r)) v = fmin(v, h - pu);
+          R.s[r] = v;
+          R.rd[r] = dval - v;
+          R.yd[r] = wq * (dval - v);
+          R.vL[r] = row_hasL(r) ? o.bound_mult_init_val : 0.0;
+          R.vU[r] = row_hasU(r) ? o.bound_mult_init_val : 0.0;
+        }
+        for (int a = 0; a < 7; ++a) y0[a] = 0.0;
+        mu = fmax(mu, warp_max(vmax));
+        tau = fmax(o.tau_min, 1.0 - mu);
+        zeta = sqrt(mu);
+        df = 1.0;
+        mu_floor = fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0));
+        filt_n = 0;
+        acc_count = 0;
+        resto_ = true;
+        resto_it = 0;
+        alpha = 0.0;
+        phase = kPhInit2;          // evaluate the start point with the restoration objective
+      }
       // ================= A. derivatives, convergence tests, barrier update ===============
       if (phase == kPhInit || phase == kPhNewton) {
         eval_derivs(phase == kPhInit ? 1 : 0);
-        if (phase == kPhInit) {
+        if (phase == kPhInit && reinit) {
+          // multiplier re-initialisation after restoration: scaling, bounds and mu stay as they are
+        } else if (phase == kPhInit) {
           // ---- gradient-based scaling at the starting point ----------------------------
           double sig_n_raw = shfl(sigc_prev, next_lane());
           double sig_n = (lane == N - 1) ? 0.0 : sig_n_raw;
@@ -1189,12 +1342,13 @@ struct WarpSolver {
             if (!finite_d(E0)) {
               status = kInvalidNumber;
               done = true;
-            } else if (E0 <= o.tol && e.dual_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol &&
+            } else if (E0 <= o.tol && e.dual_inf / df <= o.dual_inf_tol && (in_resto() || viol <= o.constr_viol_tol) &&
                        cmp0 / df <= o.compl_inf_tol) {
-              status = kSolveSucceeded;
+              // restoration: a stationary point of the infeasibility measure that the filter rejects
+              status = in_resto() ? kRestorationNeeded : kSolveSucceeded;
               done = true;
             } else {
-              if (E0 <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
+              if (!in_resto() && E0 <= o.acceptable_tol && e.dual_inf / df <= o.acceptable_dual_inf_tol &&
                   viol <= o.acceptable_constr_viol_tol && cmp0 / df <= o.acceptable_compl_inf_tol) {
                 acc_count++;
                 if (acc_count >= o.acceptable_iter) {
@@ -1243,7 +1397,7 @@ struct WarpSolver {
         }
         if (failed) { status = kErrorInStepComputation; break; }
         double gs_ds, th_loc;
-        const double a_new = slack_steps(rdv, gs_ds, th_loc);     // dsr = J_d dx + rdv ; FTB step
+        const double a_new = slack_steps(rdv, dwu, gs_ds, th_loc);     // dsr = J_d dx + rdv ; FTB step
         if (phase == kPhInit) {
           // ---- least-squares multipliers: y = -(QP multipliers), yd = (vU - vL) - J_d dx ----
           double ymax = 0.0;
@@ -1277,7 +1431,11 @@ struct WarpSolver {
           double g = gs_ds;
           {
             const double dup1 = shfl(du[1], prev_lane());
-            if (act) {
+            if (act && in_resto()) {
+              const double d9[9] = {dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dsh, du[0], du[1]};
+#pragma unroll 1
+              for (int a = 0; a < 9; ++a) g += R.pg[a] * d9[a];
+            } else if (act) {
               g += gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
                    gcost[4] * dx[4];
               if (lane >= 1) g += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
@@ -1308,7 +1466,11 @@ struct WarpSolver {
             for (int r = 0; r < kNumRows; ++r) R.dsr[r] = sv_dsr[r];
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
-            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+            if (!(alpha >= amin && n_ls < 60)) {
+              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
           } else {
             a_soc = a_new;
           }
@@ -1316,14 +1478,43 @@ struct WarpSolver {
       }
       // ================= C. trial point (single call site) =======================================
       {
-        const double at = (phase == kPhSoc) ? a_soc : alpha;
+        const bool check = (phase == kPhRestoCheck);
+        const double at = check ? 0.0 : ((phase == kPhSoc) ? a_soc : alpha);
         for (int a = 0; a < 6; ++a) tp.x[a] = x[a] + at * dx[a];
         tp.sh = sh + at * dsh;
         tp.u[0] = u[0] + at * du[0];
         tp.u[1] = u[1] + at * du[1];
-        eval_point(tp, tp_rd, at);
+        eval_point(tp, tp_rd, at, in_resto() && !check, check ? R.osave[2] : df);
       }
       // ================= D. decisions ===========================================================
+      if (RESTO && phase == kPhRestoCheck) {
+        // ---- leave the restoration phase?  The point must be acceptable to the ORIGINAL filter and
+        //      have reduced the original infeasibility by kappa_resto ------------------------------
+        bool leave = tp.finite && tp.theta <= o.kappa_resto * theta_R && tp.theta <= R.osave[3];
+        if (leave)
+          leave = filter_ok_in(tp.theta, tp.f + R.osave[0] * tp.barB, R.osave[6], R.osave[7], (int)R.osave[8]);
+        if (leave) {
+          resto_ = false;
+          mu = R.osave[0]; tau = R.osave[1]; df = R.osave[2]; theta_max = R.osave[3]; theta_min = R.osave[4];
+          mu_floor = R.osave[5]; filt_th = R.osave[6]; filt_ph = R.osave[7]; filt_n = (int)R.osave[8];
+          acc_count = (int)R.osave[9];
+#pragma unroll 1
+          for (int r = 0; r < kNumRows; ++r) {
+            R.vL[r] = (on(r) && row_hasL(r)) ? o.bound_mult_init_val : 0.0;
+            R.vU[r] = (on(r) && row_hasU(r)) ? o.bound_mult_init_val : 0.0;
+          }
+          reinit = true;           // least-squares multipliers at the restored point, then resume
+          phase = kPhInit;
+          continue;
+        }
+        if (resto_it >= o.resto_max_iter) { status = kRestorationNeeded; break; }
+        phase = kPhNewton;
+        continue;
+      }
+      if (phase == kPhInit && reinit) {
+        phase = kPhInit2;          // the slacks of the restored point are kept
+        continue;
+      }
       if (phase == kPhInit) {
         // slacks pushed into their (relaxed) bounds; tp.rd holds the row values (s was 0)
 #pragma unroll 1
@@ -1353,8 +1544,11 @@ struct WarpSolver {
         fval = tp.f;
         barB = tp.barB;
         cur_finite = tp.finite;
-        theta_max = o.theta_max_fact * fmax(1.0, tp.theta);
-        theta_min = o.theta_min_fact * fmax(1.0, tp.theta);
+        if (!reinit) {
+          theta_max = o.theta_max_fact * fmax(1.0, tp.theta);
+          theta_min = o.theta_min_fact * fmax(1.0, tp.theta);
+        }
+        reinit = false;
         phase = kPhNewton;
         continue;
       }
@@ -1390,7 +1584,11 @@ struct WarpSolver {
             for (int r = 0; r < kNumRows; ++r) R.dsr[r] = sv_dsr[r];
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
-            if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+            if (!(alpha >= amin && n_ls < 60)) {
+              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
           } else {
             th_old = tp.theta;
             for (int a = 0; a < 6; ++a) c_soc[a] = a_soc * c_soc[a] + tp.c[a];
@@ -1423,7 +1621,11 @@ struct WarpSolver {
         }
         alpha *= o.alpha_red_factor;
         phase = kPhBacktrack;
-        if (!(alpha >= amin && n_ls < 60)) { status = kRestorationNeeded; break; }
+        if (!(alpha >= amin && n_ls < 60)) {
+              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
+              status = kRestorationNeeded;
+              break;
+            }
         continue;
       }
       // ================= E. accept the trial point ===============================================
@@ -1481,10 +1683,12 @@ struct WarpSolver {
         }
         R.s[r] = snew;
         R.rd[r] = tp_rd[r];
+        if (in_resto()) R.yd[r] = wq * tp_rd[r];
       }
       last_alpha = astep;
       it++;
-      phase = kPhNewton;
+      if (in_resto()) resto_it++;
+      phase = in_resto() ? kPhRestoCheck : kPhNewton;
     }
 
     // ---- outputs ---------------------------------------------------------------------------
@@ -1550,7 +1754,7 @@ MPCR_HD int lam_g_stride(const Config& c) {
   return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
 }
 
-template <int MODEL, bool SG = false>
+template <int MODEL, bool SG = false, bool RESTO = false>
 MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                           int trace_rows, double* wsbase, double* stagebase) {
   const int N = cfg.N;
@@ -1592,12 +1796,18 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     syncwarp();
   }
   RowState rows;
-  WarpSolver<MODEL, SG> solver(cfg, prm, pv, rows, wsbase, stagebase);
+  WarpSolver<MODEL, SG, RESTO> solver(cfg, prm, pv, rows, wsbase, stagebase);
   solver.solve(so);
 }
 
 MPCR_D void solve_problem_any(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                               int trace_rows, double* wsbase, double* stagebase) {
+  if (cfg.o.restoration) {
+    if (cfg.model == kDynamic) solve_problem<kDynamic, false, true>(cfg, in, out, b, trace_rows, wsbase, stagebase);
+    else if (cfg.model == kKinematic) solve_problem<kKinematic, false, true>(cfg, in, out, b, trace_rows, wsbase, stagebase);
+    else solve_problem<kBlended, false, true>(cfg, in, out, b, trace_rows, wsbase, stagebase);
+    return;
+  }
   if (cfg.model == kDynamic) solve_problem<kDynamic>(cfg, in, out, b, trace_rows, wsbase, stagebase);
   else if (cfg.model == kKinematic) solve_problem<kKinematic>(cfg, in, out, b, trace_rows, wsbase, stagebase);
   else solve_problem<kBlended>(cfg, in, out, b, trace_rows, wsbase, stagebase);

@@ -92,3 +92,22 @@ def test_failure_status_is_reported_not_raised():
     # both report a failure status (the exact code on a diverging path is not compared)
     assert int(out['status'][0]) < 0 and ref['status'] < 0
     assert np.isfinite(out['U']).all() and np.isfinite(out['X']).all()
+
+
+def test_restoration_phase_in_the_warp_solver():
+    """mpcr_config.restoration: the warp solver's restoration build against the oracle's
+    restoration study (oracle/restoration.py, RestoQuadNLP) and the independent optimum."""
+    d = load_fixture("cfg3_t1_triple_512.npz")
+    idx = [478, 499]
+    a = lambda k: d[k][idx]
+    plain = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), max_err=a('max_err'), lane_constraint=1)
+    assert (plain['status'] == -2).all()
+    out = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), max_err=a('max_err'), lane_constraint=1,
+                    restoration=1)
+    assert (out['status'] == 0).all()
+    for j, b in enumerate(idx):
+        ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], lane=True,
+                           max_error=float(d['max_err'][b]), options=dict(restoration='quad'))
+        assert ref['status'] == 0
+        assert abs(out['obj'][j] - ref['obj']) <= 1e-6 * abs(ref['obj'])
+    assert abs(out['obj'][0] - (-112828.3055199883)) <= 1e-6 * 112828.3

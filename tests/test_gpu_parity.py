@@ -231,10 +231,9 @@ def test_rk4_integrator_on_gpu(cfg2):
         assert_parity(res, j, ref)
 
 
-def test_restoration_rescue_pass_on_gpu():
-    """mpcr_config.restoration on the GPU: the warp kernel's status -2 problems are re-solved by the
-    lane kernel with the feasibility-restoration phase (rescue pass); with solve_kernel = lanes the
-    phase runs in place.  Config 3 (lane rows): 25 of 512 problems need it."""
+def test_restoration_phase_on_gpu():
+    """mpcr_config.restoration on the GPU (both kernels carry the feasibility-restoration phase):
+    config 3 (lane rows) has 24 of 512 problems on which the plain filter line search gives up."""
     import os
     from mpc_racing_b200.solver import BatchedMPC
     d = load_fixture("cfg3_t1_triple_512.npz")
@@ -246,13 +245,16 @@ def test_restoration_rescue_pass_on_gpu():
         *args, max_err=d['max_err'])
     assert (plain.status == -2).sum() >= 20
     assert (resc.status >= 0).mean() >= 0.995 and (lanes.status >= 0).mean() >= 0.995
+    # problems that never needed it: same answers (the restoration build is a separate compilation)
     untouched = plain.status >= 0
-    assert np.array_equal(resc.U[untouched], plain.U[untouched])          # the rescue pass only touches failures
+    assert (resc.iters[untouched] == plain.iters[untouched]).mean() >= 0.97
+    same = untouched & (resc.iters == plain.iters)
+    assert np.abs(resc.U[same] - plain.U[same]).max() <= 1e-7
     both = (resc.status >= 0) & (lanes.status >= 0)
     rel = np.abs(resc.obj - lanes.obj)[both] / np.abs(lanes.obj[both])
-    assert (rel <= 1e-6).mean() >= 0.99
-    # a rescued problem against the oracle's restoration study and the independent optimum
+    assert (rel <= 1e-6).mean() >= 0.98
+    # a rescued problem against the independent optimum (scipy trust-constr) of the oracle study
     b = 478
-    assert plain.status[b] == -2 and resc.status[b] == 0
+    assert plain.status[b] == -2 and g['status'][b] == -2 and resc.status[b] == 0 and lanes.status[b] == 0
     assert abs(resc.obj[b] - (-112828.3055199883)) <= 1e-6 * 112828.3
-    assert g['status'][b] == -2
+    assert abs(lanes.obj[b] - (-112828.3055199883)) <= 1e-6 * 112828.3
