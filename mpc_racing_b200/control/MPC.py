@@ -21,15 +21,15 @@ from .ControllerParameters import FixedControllerParameters, RuntimeControllerPa
 _SOLVERS = {}
 
 
-def _solver_for(N, Ts, fixed, model, wrap, device):
-    key = (N, Ts, model, wrap, device) + tuple(
+def _solver_for(N, Ts, fixed, model, wrap, device, restoration):
+    key = (N, Ts, model, wrap, device, restoration) + tuple(
         getattr(fixed, k) for k in ("lambda_s", "alpha_L", "min_steer", "max_steer", "min_throttle",
                                     "max_steer_delta", "min_steer_delta", "max_throttle_delta",
                                     "min_throttle_delta", "q_v_max", "v_max"))
     s = _SOLVERS.get(key)
     if s is None:
         s = BatchedMPC(N=N, Ts=Ts, model=model, fixed_params=fixed, wrap_constraint=wrap,
-                       device=device, on_device=False)
+                       device=device, on_device=False, restoration=restoration)
         _SOLVERS[key] = s
     return s
 
@@ -49,6 +49,7 @@ class MPCSolution:
 class MPC:
     model = "dynamic"        # control/MPC.py:83 always uses f_vehicle (the dynamic model)
     wrap_constraint = True   # control/MPC.py:142-143 at i = 0
+    restoration = True       # IPOPT always has its restoration phase; here: mpcr_config.restoration
     device = 0
 
     def __init__(self,
@@ -69,7 +70,7 @@ class MPC:
         N = self.fixed_params.N if N is None else int(N)
         Ts = FixedControllerParameters.Ts if Ts is None else Ts
         solver = _solver_for(N, float(Ts), self.fixed_params, self.model, self.wrap_constraint,
-                             self.device)
+                             self.device, self.restoration)
         nan = float("nan")
         x0 = np.array([[state0.x, state0.y, state0.yaw, state0.v_x, state0.v_y, state0.yaw_dot]],
                       dtype=np.float64)
