@@ -94,7 +94,7 @@ def test_restoration_phase_rescues_lane_row_failures():
     accepts a point with theta reduced by kappa_resto, then resumes.  The oracle's
     restoration study (oracle/restoration.py, RestoQuadNLP) reaches the same optima."""
     d = load_fixture("cfg3_t1_triple_512.npz")
-    idx = [28, 478, 499]                     # status -2 without restoration (tests/golden/*_oracle.npz)
+    idx = [478, 499]                         # status -2 without restoration (tests/golden/*_oracle.npz)
     a = lambda k: d[k][idx]
     plain = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), max_err=a('max_err'), lane_constraint=1,
                       lanes=True)
@@ -110,7 +110,7 @@ def test_restoration_phase_rescues_lane_row_failures():
         dU = np.abs(out['U'][j] - ref['U'])
         dU[0, -1] = 0.0
         assert dU.max() <= 2e-3, (b, dU.max())      # different restoration paths, same optimum
-    assert abs(out['obj'][1] - (-112828.3055199883)) <= 1e-6 * 112828.3     # scipy trust-constr optimum of #478
+    assert abs(out['obj'][0] - (-112828.3055199883)) <= 1e-6 * 112828.3     # scipy trust-constr optimum of #478
     # problems that do not need it are untouched by the option
     cfg2 = load_fixture("cfg2_shanghai_4096.npz")
     i = [0, 1, 2]
