@@ -13,8 +13,10 @@ so every inequality row gets a slack (d(x) - s = 0, dL <= s <= dU) and x itself
 has no bounds.
 
 Deliberate simplifications (documented in DESIGN.md, shared by the CUDA path):
-  * no restoration phase: when the line search cannot find an acceptable step
-    the solve stops with status RESTORATION_NEEDED (a failure status);
+  * restoration phase: IPOPT's l1 feasibility NLP is replaced by a quadratic-penalty variant over the
+    same variables (options['restoration'] = True, off by default - the solve then stops with
+    status RESTORATION_NEEDED, a failure status - restated inline below exactly as the kernels do
+    it; oracle/restoration.py holds the studies of IPOPT's own formulation);
   * no watchdog procedure, no "tiny step" heuristics, no slack re-basing
     (IPOPT's slack_move);
   * the linear solver is a dense LDL^T (scipy) whose inertia is read from the
@@ -52,8 +54,10 @@ DEFAULT_OPTIONS = dict(
     # inertia correction
     delta_w_init=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_minus=1.0 / 3.0, kappa_w_plus=8.0, kappa_w_plus_first=100.0,
-    # EXPERIMENTAL (study only, not mirrored by the kernels): IPOPT's restoration phase, oracle/restoration.py
-    restoration=False, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True, resto_quad_weight=1.0,
+    # restoration: True = the kernels' feasibility-restoration phase (quadratic penalty over the same (x, s),
+    # DESIGN.md section 3), restated below; 'l1' / 'quad' = the studies of oracle/restoration.py (IPOPT's l1
+    # formulation / the penalty variant as a nested NLP), which the kernels do not mirror
+    restoration=False, resto_weight=1.0, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True, resto_quad_weight=1.0,
 )
 
 
@@ -183,11 +187,14 @@ def solve(nlp, options=None, trace=None, stop=None):
         J = nlp.jac(xx)
         return dc_s[:, None] * J[ic], dd_s[:, None] * J[idn]
 
-    def hess(xx, yc, yd):
+    def _lam_of(yc, yd):
         lam = np.zeros(m)
         lam[ic] = yc * dc_s
         lam[idn] = yd * dd_s
-        return nlp.hess(xx, df, lam)
+        return lam
+
+    def hess(xx, yc, yd):
+        return nlp.hess(xx, df, _lam_of(yc, yd))
 
     # ---- starting point: slacks pushed into their bounds -----------------------
     fval, c, d = evals(x)
@@ -229,15 +236,17 @@ def solve(nlp, options=None, trace=None, stop=None):
         phi += kd * mu_ * (np.sum(sl[onlyL]) + np.sum(su[onlyU]))
         return phi
 
-    def theta_of(cc, dd, ss):
-        return np.sum(np.abs(cc)) + np.sum(np.abs(dd - ss))
+    def theta_of(cc, dd, ss, inner=False):
+        return np.sum(np.abs(cc)) + (0.0 if inner else np.sum(np.abs(dd - ss)))
 
     def errors(mu_, gf_, Jc_, Jd_, c_, d_, s_, yc_, yd_, vL_, vU_):
         sl, su = slacks(s_)
         rx = gf_ + Jc_.T @ yc_ + Jd_.T @ yd_
         rs = -yd_ - vL_ + vU_
         dual_inf = max(np.max(np.abs(rx), initial=0.0), np.max(np.abs(rs), initial=0.0))
-        pr_inf = max(np.max(np.abs(c_), initial=0.0), np.max(np.abs(d_ - s_), initial=0.0))
+        pr_inf = np.max(np.abs(c_), initial=0.0)
+        if not resto:
+            pr_inf = max(pr_inf, np.max(np.abs(d_ - s_), initial=0.0))
         compl = max(np.max(np.abs(sl * vL_ - mu_)[hasL], initial=0.0),
                     np.max(np.abs(su * vU_ - mu_)[hasU], initial=0.0))
         nb = int(hasL.sum() + hasU.sum())
@@ -260,10 +269,46 @@ def solve(nlp, options=None, trace=None, stop=None):
     n_fact = 0
     ls_total = 0
     n_resto = 0
+    resto = False
+    resto_it = 0
+    wq = o['resto_weight']
+    zeta = 0.0
+    x_R = None
+    DR2 = None
+    saved = None
+    theta_R = 0.0
+
+    def f_resto(xx, dd, ss):
+        return 0.5 * wq * np.sum((dd - ss) ** 2) + 0.5 * zeta * np.sum(DR2 * (xx - x_R) ** 2)
 
     while True:
-        gf = df * nlp.grad_f(x)
+        gf = zeta * DR2 * (x - x_R) if resto else df * nlp.grad_f(x)
         Jc, Jd = jacs(x)
+        if resto and resto_it >= 1:
+            # ---- leave the restoration phase?  acceptable to the ORIGINAL filter, theta reduced ------
+            fo = df * nlp.f(x)
+            th_o = theta_of(c, d, s)
+            mu_o, tau_o, thmax_o, thmin_o, filt_o, acc_o = saved
+            leave = np.isfinite(fo) and th_o <= o['kappa_resto'] * theta_R and th_o <= thmax_o
+            if leave:
+                ph_o = barrier_obj(fo, s, mu_o)
+                leave = np.isfinite(ph_o) and all((th_o <= tf or ph_o <= pf) for (tf, pf) in filt_o)
+            if leave:
+                resto = False
+                mu, tau, theta_max, theta_min, filt, acceptable_count = mu_o, tau_o, thmax_o, thmin_o, filt_o, acc_o
+                vL = np.where(hasL, o['bound_mult_init_val'], 0.0)
+                vU = np.where(hasU, o['bound_mult_init_val'], 0.0)
+                gf = df * nlp.grad_f(x)
+                kk = _KKT(np.zeros((n, n)), Jc, Jd, np.zeros(md), 1.0)
+                _, _, yc, yd = kk.solve(gf, vU - vL, np.zeros(mc), np.zeros(md))
+                yc, yd = -yc, -yd
+                if max(np.max(np.abs(yc), initial=0.0), np.max(np.abs(yd), initial=0.0)) > o['constr_mult_init_max']:
+                    yc[:] = 0.0
+                    yd[:] = 0.0
+                fval = fo
+            elif resto_it >= o['resto_max_iter']:
+                status = RESTORATION_NEEDED
+                break
         if not (np.all(np.isfinite(gf)) and np.all(np.isfinite(Jc)) and np.all(np.isfinite(Jd))
                 and np.isfinite(fval)):
             status = INVALID_NUMBER
@@ -276,14 +321,16 @@ def solve(nlp, options=None, trace=None, stop=None):
         gg = nlp.g(x)
         viol = max(np.max(np.maximum(nlp.gl - gg, 0.0), initial=0.0),
                    np.max(np.maximum(gg - nlp.gu, 0.0), initial=0.0))
+        dfe = 1.0 if resto else df          # the restoration objective is not rescaled
         if trace is not None:
-            trace.append(dict(it=it, obj=fval / df, E0=E0, dual_inf=dual_inf, pr_inf=pr_inf,
+            trace.append(dict(it=it, obj=fval / dfe, E0=E0, dual_inf=dual_inf, pr_inf=pr_inf,
                               compl=compl0, mu=mu, x=x.copy()))
-        if (E0 <= o['tol'] and dual_inf / df <= o['dual_inf_tol'] and viol <= o['constr_viol_tol']
-                and compl0 / df <= o['compl_inf_tol']):
-            status = SOLVE_SUCCEEDED
+        if (E0 <= o['tol'] and dual_inf / dfe <= o['dual_inf_tol'] and (resto or viol <= o['constr_viol_tol'])
+                and compl0 / dfe <= o['compl_inf_tol']):
+            # restoration: a stationary point of the infeasibility measure that the filter rejects
+            status = RESTORATION_NEEDED if resto else SOLVE_SUCCEEDED
             break
-        if (E0 <= o['acceptable_tol'] and dual_inf / df <= o['acceptable_dual_inf_tol']
+        if (not resto and E0 <= o['acceptable_tol'] and dual_inf / df <= o['acceptable_dual_inf_tol']
                 and viol <= o['acceptable_constr_viol_tol']
                 and compl0 / df <= o['acceptable_compl_inf_tol']):
             acceptable_count += 1
@@ -297,7 +344,7 @@ def solve(nlp, options=None, trace=None, stop=None):
             break
 
         # ---- barrier parameter update (monotone) --------------------------------
-        mu_floor = max(o['mu_min'], min(o['tol'], o['compl_inf_tol'] * df) / (o['barrier_tol_factor'] + 1))
+        mu_floor = max(o['mu_min'], min(o['tol'], o['compl_inf_tol'] * dfe) / (o['barrier_tol_factor'] + 1))
         while True:
             Emu = errors(mu, gf, Jc, Jd, c, d, s, yc, yd, vL, vU)[0]
             if Emu <= o['barrier_tol_factor'] * mu and mu > mu_floor:
@@ -312,12 +359,25 @@ def solve(nlp, options=None, trace=None, stop=None):
         sl, su = slacks(s)
         sig_s = np.where(hasL, vL / sl, 0.0) + np.where(hasU, vU / su, 0.0)
         H = hess(x, yc, yd)
-        rx = gf + Jc.T @ yc + Jd.T @ yd
         gs_bar = (-np.where(hasL, mu / sl, 0.0) + np.where(hasU, mu / su, 0.0)
                   + kd * mu * (onlyL.astype(float) - onlyU.astype(float)))
-        rs = gs_bar - yd
+        if resto:
+            # rows in the objective (yd = wq (d - s) carries their curvature weights in H): eliminating
+            # ds from  wq/2 (Jd dx - ds + rd)^2 + (Sigma + dw)/2 ds^2 + gs_bar ds  scales the row's
+            # condensed terms by kappa = wq / (wq + Sigma + dw)
+            H = nlp.hess(x, 0.0, _lam_of(yc, yd)) + np.diag(zeta * DR2)
+            rx = gf + Jc.T @ yc
+            rs = None
+
+            def resto_kkt(dw_):
+                Dt = sig_s + dw_
+                kap = wq / (wq + Dt)
+                return _KKT(H, Jc, Jd, kap * Dt - dw_, dw_), kap, Dt
+        else:
+            rx = gf + Jc.T @ yc + Jd.T @ yd
+            rs = gs_bar - yd
         dw = 0.0
-        kkt = _KKT(H, Jc, Jd, sig_s, dw)
+        kkt = resto_kkt(dw)[0] if resto else _KKT(H, Jc, Jd, sig_s, dw)
         n_fact += 1
         first_try = True
         failed = False
@@ -333,14 +393,24 @@ def solve(nlp, options=None, trace=None, stop=None):
             if dw > o['delta_w_max']:
                 failed = True
                 break
-            kkt = _KKT(H, Jc, Jd, sig_s, dw)
+            kkt = resto_kkt(dw)[0] if resto else _KKT(H, Jc, Jd, sig_s, dw)
             n_fact += 1
         if failed:
             status = ERROR_IN_STEP_COMPUTATION
             break
         if dw > 0.0:
             dw_last = dw
-        dx, ds, dyc, dyd = kkt.solve(-rx, -rs, -c, -(d - s))
+        if resto:
+            _, kap, Dt = resto_kkt(dw)
+
+            def resto_solve(c_rhs, d_rhs):
+                e_eff = kap * (Dt * d_rhs + gs_bar)
+                dx_, _, dyc_, _ = kkt.solve(-rx, -e_eff, -c_rhs, np.zeros(md))
+                ds_ = kap * (Jd @ dx_ + d_rhs) - gs_bar / (wq + Dt)
+                return dx_, ds_, dyc_, np.zeros(md)
+            dx, ds, dyc, dyd = resto_solve(c, d - s)
+        else:
+            dx, ds, dyc, dyd = kkt.solve(-rx, -rs, -c, -(d - s))
         dvL = np.where(hasL, mu / sl - vL - vL / sl * ds, 0.0)
         dvU = np.where(hasU, mu / su - vU + vU / su * ds, 0.0)
 
@@ -354,9 +424,11 @@ def solve(nlp, options=None, trace=None, stop=None):
         alpha_z = min(max_step(vL, dvL, hasL), max_step(vU, dvU, hasU))
 
         # ---- filter line search -------------------------------------------------
-        theta = theta_of(c, d, s)
+        theta = theta_of(c, d, s, resto)
         phi = barrier_obj(fval, s, mu)
         gphi_d = gf @ dx + gs_bar @ ds
+        if resto:
+            gphi_d += wq * (d - s) @ (Jd @ dx - ds)
         if gphi_d < 0:
             amin = min(o['gamma_theta'], o['gamma_phi'] * theta / (-gphi_d))
             if theta <= theta_min:
@@ -383,10 +455,12 @@ def solve(nlp, options=None, trace=None, stop=None):
             xt = x + alpha * dx_c
             st = s + alpha * ds_c
             ft, ct, dt = evals(xt)
+            if resto:
+                ft = f_resto(xt, dt, st)
             n_ls += 1
             ok = np.isfinite(ft) and np.all(np.isfinite(ct)) and np.all(np.isfinite(dt))
             if ok:
-                tht = theta_of(ct, dt, st)
+                tht = theta_of(ct, dt, st, resto)
                 pht = barrier_obj(ft, st, mu)
                 ok = np.isfinite(pht) and tht <= theta_max
             if ok:
@@ -407,20 +481,23 @@ def solve(nlp, options=None, trace=None, stop=None):
                 break
             # second-order correction on the first trial step
             if (not soc_done and n_ls == 1 and np.isfinite(ft) and np.all(np.isfinite(ct))
-                    and theta_of(ct, dt, st) >= theta):
+                    and theta_of(ct, dt, st, resto) >= theta):
                 soc_done = True
                 c_soc = alpha * c + ct
                 d_soc = alpha * (d - s) + (dt - st)
                 th_old = theta
                 for _ in range(o['max_soc']):
-                    dxs, dss, dycs, dyds = kkt.solve(-rx, -rs, -c_soc, -d_soc)
+                    dxs, dss, dycs, dyds = (resto_solve(c_soc, d_soc) if resto
+                                            else kkt.solve(-rx, -rs, -c_soc, -d_soc))
                     a_soc = min(max_step(sl, dss, hasL), max_step(su, -dss, hasU))
                     xt = x + a_soc * dxs
                     st = s + a_soc * dss
                     ft, ct, dt = evals(xt)
+                    if resto:
+                        ft = f_resto(xt, dt, st)
                     if not (np.isfinite(ft) and np.all(np.isfinite(ct))):
                         break
-                    tht = theta_of(ct, dt, st)
+                    tht = theta_of(ct, dt, st, resto)
                     pht = barrier_obj(ft, st, mu)
                     if not np.isfinite(pht) or tht > theta_max:
                         break
@@ -450,7 +527,33 @@ def solve(nlp, options=None, trace=None, stop=None):
                     break
             alpha *= o['alpha_red_factor']
         ls_total += n_ls
-        if not accepted and o['restoration']:
+        if not accepted and o['restoration'] is True and not resto:
+            # ---- enter the restoration phase at the current iterate (x_R, s_R): the kernels' text ------
+            theta_R = theta
+            filt.append(((1 - o['gamma_theta']) * theta, phi - o['gamma_phi'] * theta))
+            saved = (mu, tau, theta_max, theta_min, filt, acceptable_count)
+            x_R = x.copy()
+            DR2 = (1.0 / np.maximum(1.0, np.abs(x_R))) ** 2
+            vmax = max(np.max(np.abs(c), initial=0.0), np.max(np.abs(d - s), initial=0.0))
+            s = np.where(hasL, np.maximum(s, dL + pL), s)
+            s = np.where(hasU, np.minimum(s, dU - pU), s)
+            vL = np.where(hasL, o['bound_mult_init_val'], 0.0)
+            vU = np.where(hasU, o['bound_mult_init_val'], 0.0)
+            yc = np.zeros(mc)
+            yd = wq * (d - s)
+            mu = max(mu, vmax)
+            tau = max(o['tau_min'], 1.0 - mu)
+            zeta = np.sqrt(mu)
+            filt = []
+            acceptable_count = 0
+            resto = True
+            resto_it = 0
+            fval = f_resto(x, d, s)
+            th0 = theta_of(c, d, s, True)
+            theta_max = o['theta_max_fact'] * max(1.0, th0)
+            theta_min = o['theta_min_fact'] * max(1.0, th0)
+            continue
+        if not accepted and o['restoration'] in ('l1', 'quad'):
             from .restoration import RestoNLP
             theta_R, phi_R = theta, phi
             filt.append(((1 - o['gamma_theta']) * theta_R, phi_R - o['gamma_phi'] * theta_R))
@@ -512,7 +615,10 @@ def solve(nlp, options=None, trace=None, stop=None):
         x, s = xt, st
         fval, c, d = ft, ct, dt
         yc = yc + alpha * dyc_c
-        yd = yd + alpha * dyd_c
+        yd = wq * (d - s) if resto else yd + alpha * dyd_c
+        if resto:
+            resto_it += 1
+            n_resto += 1
         vL = vL + alpha_z * dvL
         vU = vU + alpha_z * dvU
         sl, su = slacks(s)

@@ -1,4 +1,5 @@
-"""Oracle (test infrastructure, EXPERIMENTAL STUDY - off by default, not mirrored by the kernels):
+"""Oracle (test infrastructure): STUDIES of the restoration phase - the kernels' phase itself is restated
+inline in oracle/ipm.py (options['restoration'] = True).  Here:
 IPOPT's feasibility-restoration phase (RestoMinC_1Nrm) restated for the dense oracle.
 
 When the filter line search fails, IPOPT minimises the l1 constraint violation
@@ -10,7 +11,8 @@ When the filter line search fails, IPOPT minimises the l1 constraint violation
 algorithm, until a point is acceptable to the ORIGINAL filter and has reduced the original
 infeasibility theta by the factor kappa_resto = 0.9; the regular algorithm then resumes from that
 point with least-squares multipliers.  This file builds that NLP around the scaled constraint
-functions of the outer problem; oracle/ipm.py calls it when options['restoration'] is set.
+functions of the outer problem; oracle/ipm.py calls it with options['restoration'] = 'l1' (this class)
+or 'quad' (RestoQuadNLP below: the penalty variant the kernels use, as a nested NLP).
 """
 import numpy as np
 

@@ -19,6 +19,8 @@ CASES = {
     "cfg2_shanghai_4096": dict(N=30, Ts=0.05, lane=False),
     "cfg3_t1_triple_512": dict(N=30, Ts=0.05, lane=True),
     "prod_t4_256": dict(N=15, Ts=0.05, lane=False),
+    # the lane-row batch once more with the restoration phase (mpcr_config.restoration)
+    "cfg3_t1_triple_512+resto": dict(N=30, Ts=0.05, lane=True, restoration=True),
 }
 
 
@@ -35,7 +37,8 @@ def _one(args):
     from parity_util import oracle_solve
     x0, up, s0, cx, cy, me, kw = args
     extra = dict(lane=True, max_error=float(me)) if kw["lane"] else {}
-    r = oracle_solve(x0, up, s0, cx, cy, N=kw["N"], Ts=kw["Ts"], **extra)
+    opts = dict(restoration=True) if kw.get("restoration") else None
+    r = oracle_solve(x0, up, s0, cx, cy, N=kw["N"], Ts=kw["Ts"], options=opts, **extra)
     return r["status"], r["iters"], r["obj"], r["U"]
 
 
@@ -44,13 +47,16 @@ def main():
     cores = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
     ctx = get_context("fork")
     with ctx.Pool(cores, initializer=_init) as pool:
+        only = sys.argv[2] if len(sys.argv) > 2 else None
         for name, kw in CASES.items():
-            d = load_fixture(name + ".npz")
+            if only and name != only:
+                continue
+            d = load_fixture(name.split("+")[0] + ".npz")
             B = d["x0"].shape[0]
             jobs = [(d["x0"][b], d["u_prev"][b], d["s0"][b], d["cx"][b], d["cy"][b], d["max_err"][b], kw)
                     for b in range(B)]
             res = pool.map(_one, jobs, chunksize=4)
-            np.savez_compressed(os.path.join(HERE, name + "_oracle.npz"),
+            np.savez_compressed(os.path.join(HERE, name.replace("+", "_") + "_oracle.npz"),
                                 status=np.array([r[0] for r in res], dtype=np.int32),
                                 iters=np.array([r[1] for r in res], dtype=np.int32),
                                 obj=np.array([r[2] for r in res]),

@@ -107,7 +107,7 @@ def test_restoration_phase_in_the_warp_solver():
     assert (out['status'] == 0).all()
     for j, b in enumerate(idx):
         ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], lane=True,
-                           max_error=float(d['max_err'][b]), options=dict(restoration='quad'))
+                           max_error=float(d['max_err'][b]), options=dict(restoration=True))
         assert ref['status'] == 0
         assert abs(out['obj'][j] - ref['obj']) <= 1e-6 * abs(ref['obj'])
     assert abs(out['obj'][0] - (-112828.3055199883)) <= 1e-6 * 112828.3

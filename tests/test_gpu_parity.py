@@ -187,6 +187,7 @@ def test_lane_kernel_matches_warp_kernel_and_oracle(cfg2):
 
 @pytest.mark.parametrize("name,kw,N", [("cfg2_shanghai_4096", {}, 30),
                                        ("cfg3_t1_triple_512", dict(lane_constraint=True), 30),
+                                       ("cfg3_t1_triple_512_resto", dict(lane_constraint=True, restoration=True), 30),
                                        ("prod_t4_256", {}, 15)])
 def test_whole_batches_against_oracle_golden(name, kw, N):
     """EVERY problem of BASELINE config 2 (4096), config 3 (512, lane rows) and the production
@@ -199,8 +200,10 @@ def test_whole_batches_against_oracle_golden(name, kw, N):
     1e-3 level (objective still equal to 1e-6) and a handful of different local minima."""
     import os
     from mpc_racing_b200.solver import BatchedMPC
-    d = load_fixture(name + ".npz")
+    d = load_fixture(name.replace("_resto", "") + ".npz")
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + "_oracle.npz"))
+    if "resto" in name:
+        assert (g["status"] >= 0).all()      # with the restoration phase the oracle solves all 512
     r = BatchedMPC(N=N, Ts=0.05, **kw).solve(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"],
                                             max_err=d["max_err"] if kw else None)
     assert ((r.status >= 0) == (g["status"] >= 0)).mean() >= 0.995

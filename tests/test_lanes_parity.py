@@ -104,7 +104,7 @@ def test_restoration_phase_rescues_lane_row_failures():
     assert (out['status'] == 0).all()
     for j, b in enumerate(idx):
         ref = oracle_solve(d['x0'][b], d['u_prev'][b], d['s0'][b], d['cx'][b], d['cy'][b], lane=True,
-                           max_error=float(d['max_err'][b]), options=dict(restoration='quad'))
+                           max_error=float(d['max_err'][b]), options=dict(restoration=True))
         assert ref['status'] == 0
         assert abs(out['obj'][j] - ref['obj']) <= 1e-6 * abs(ref['obj']), (b, out['obj'][j], ref['obj'])
         dU = np.abs(out['U'][j] - ref['U'])

@@ -1,6 +1,8 @@
-"""STUDY (oracle only, off by default, not mirrored by the kernels yet): IPOPT's restoration phase
-restated in oracle/restoration.py rescues the lane-row problems on which the plain filter line
-search stops with status -2, and lands on the optimum an independent solver finds."""
+"""Restoration in the oracle: (i) options['restoration'] = True is the kernels' phase (quadratic
+penalty over the same (x, s), restated in oracle/ipm.py); (ii) 'l1' / 'quad' are the studies of
+oracle/restoration.py (IPOPT's l1 formulation, with and without relaxed dynamics rows, and the
+penalty variant as a nested NLP).  All of them rescue the lane-row problems on which the plain filter
+line search stops with status -2 and land on the optimum an independent solver finds."""
 import numpy as np
 
 from mpc_racing_b200.workload import load_fixture
@@ -17,8 +19,9 @@ def test_restoration_rescues_a_lane_row_failure():
                     max_error=float(d['max_err'][b]))
     plain = ipm.solve(nlp)
     assert plain.status == ipm.RESTORATION_NEEDED
-    for relax_eq in (False, True):       # False: only the inequality rows are elastic (keeps the Riccati structure)
-        r = ipm.solve(nlp, dict(restoration=True, resto_relax_eq=relax_eq))
+    for opts in (dict(restoration=True), dict(restoration='quad'),
+                 dict(restoration='l1', resto_relax_eq=False), dict(restoration='l1', resto_relax_eq=True)):
+        r = ipm.solve(nlp, opts)
         assert r.status == ipm.SOLVE_SUCCEEDED and 1 <= r.n_resto <= 20
         assert abs(r.obj - INDEPENDENT_OPTIMUM_478) <= 1e-6 * abs(INDEPENDENT_OPTIMUM_478)
         g = nlp.g(r.x)
