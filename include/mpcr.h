@@ -94,7 +94,7 @@ typedef struct mpcr_config {
   int32_t restoration;       /* 1: when the filter line search fails, run the feasibility-restoration phase
                               * (IPOPT would; quadratic-penalty variant) instead of returning
                               * MPCR_RESTORATION_FAILED.  Selects the kernel build that contains the phase
-                              * (~20 % slower per solve).  0 = off (default) */
+                              * (~6 % slower per iteration).  0 = off (default) */
   int32_t reserved_;
 } mpcr_config;
 

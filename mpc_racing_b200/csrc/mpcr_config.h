@@ -118,7 +118,7 @@ inline void config_convert(const mpcr_config& c, Config* out) {
   o.kappa_w_plus = 8.0;
   o.kappa_w_plus_first = 100.0;
   o.restoration = c.restoration;
-  o.resto_max_iter = 200;
+  o.resto_max_iter = 100;
   o.resto_weight = 1.0;
   o.kappa_resto = 0.9;
 }

@@ -257,9 +257,8 @@ struct WarpSolver {
   double filt_th, filt_ph;
   int filt_n;
   // feasibility restoration (quadratic-penalty variant, same text as LaneSolver): while `in_resto()` is set
-  // the objective is wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 and the rows' multipliers are wq (d - s)
+  // the objective is wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 and the rows' multipliers are o.resto_weight (d - s)
   bool resto_;
-  double wq, zeta;
   MPCR_D bool in_resto() const { return RESTO && resto_; }
   // packed slots of the stage-Hessian entries (r, lane), r = 0..11, one byte each (registers,
   // no runtime-indexed local array): rows 0-7 in colslot_lo, rows 8-11 in colslot_hi
@@ -384,7 +383,7 @@ struct WarpSolver {
         for (int a = 0; a < 9; ++a) {
           const double ref = R.xr[a];
           const double dr = 1.0 / fmax(1.0, fabs(ref));
-          fl += 0.5 * zeta * dr * dr * (v9[a] - ref) * (v9[a] - ref);
+          fl += 0.5 * R.osave[10] * dr * dr * (v9[a] - ref) * (v9[a] - ref);
         }
       }
       for (int k = 0; k < 6; ++k) {
@@ -398,7 +397,7 @@ struct WarpSolver {
       if (on(r)) {
         const double sv = R.s[r] + at * R.dsr[r];
         rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
-        if (inner) fl += 0.5 * wq * rdv * rdv;
+        if (inner) fl += 0.5 * o.resto_weight * rdv * rdv;
         else th += fabs(rdv);
         if (row_hasL(r)) {
           const double sl = sv - lo(r);
@@ -461,7 +460,7 @@ struct WarpSolver {
       for (int a = 0; a < 9; ++a) {
         const double ref = R.xr[a];
         const double dr = 1.0 / fmax(1.0, fabs(ref));
-        pd9[a] = act ? zeta * dr * dr : 0.0;
+        pd9[a] = act ? R.osave[10] * dr * dr : 0.0;
         R.pg[a] = pd9[a] * (v9[a] - ref);
       }
       gcost[0] = R.pg[0]; gcost[1] = R.pg[1]; gcost[2] = R.pg[6]; gcost[3] = R.pg[3]; gcost[4] = R.pg[4];
@@ -577,7 +576,7 @@ struct WarpSolver {
           er = Dr * (rdv ? rdv[r] : 0.0) + g;
           if (in_resto()) {
             // row in the objective: min over ds of wq/2 (J dx - ds + rd)^2 + Sigma/2 ds^2 + g ds
-            const double kap = wq / (wq + Dr);
+            const double kap = o.resto_weight / (o.resto_weight + Dr);
             Dr *= kap;
             er *= kap;
           }
@@ -1105,8 +1104,8 @@ struct WarpSolver {
           // slack step of a row that sits in the objective, and its share of grad(f_R)' d
           double sg, gb;
           sigma_gsb(r, sg, gb);
-          d = (wq * d - gb) / (wq + sg + dwu);
-          g += wq * R.rd[r] * (jdx - d);
+          d = (o.resto_weight * d - gb) / (o.resto_weight + sg + dwu);
+          g += o.resto_weight * R.rd[r] * (jdx - d);
         } else {
           th += fabs(R.rd[r]);
         }
@@ -1183,8 +1182,6 @@ struct WarpSolver {
     fval = 0.0;
     barB = 0.0;
     resto_ = false;
-    wq = o.resto_weight;
-    zeta = 0.0;
     {
       int nr = 0, nb = 0;
 #pragma unroll 1
@@ -1217,13 +1214,12 @@ struct WarpSolver {
     // restoration bookkeeping (the outer problem's scalars are parked in R.osave)
     bool want_resto = false, reinit = false;
     int resto_it = 0;
-    double theta_R = 0.0;
 
     while (true) {
       if (RESTO && want_resto) {
         // ---- enter the restoration phase at the current iterate (x_R, s_R) ---------------------
         want_resto = false;
-        theta_R = theta;
+        R.osave[11] = theta;
         filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);   // the start point enters the filter
         R.osave[0] = mu; R.osave[1] = tau; R.osave[2] = df; R.osave[3] = theta_max; R.osave[4] = theta_min;
         R.osave[5] = mu_floor; R.osave[6] = filt_th; R.osave[7] = filt_ph; R.osave[8] = (double)filt_n;
@@ -1259,14 +1255,14 @@ struct WarpSolver {
           if (row_hasU(r)) v = fmin(v, h - pu);
           R.s[r] = v;
           R.rd[r] = dval - v;
-          R.yd[r] = wq * (dval - v);
+          R.yd[r] = o.resto_weight * (dval - v);
           R.vL[r] = row_hasL(r) ? o.bound_mult_init_val : 0.0;
           R.vU[r] = row_hasU(r) ? o.bound_mult_init_val : 0.0;
         }
         for (int a = 0; a < 7; ++a) y0[a] = 0.0;
         mu = fmax(mu, warp_max(vmax));
         tau = fmax(o.tau_min, 1.0 - mu);
-        zeta = sqrt(mu);
+        R.osave[10] = sqrt(mu);
         df = 1.0;
         mu_floor = fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0));
         filt_n = 0;
@@ -1490,7 +1486,7 @@ struct WarpSolver {
       if (RESTO && phase == kPhRestoCheck) {
         // ---- leave the restoration phase?  The point must be acceptable to the ORIGINAL filter and
         //      have reduced the original infeasibility by kappa_resto ------------------------------
-        bool leave = tp.finite && tp.theta <= o.kappa_resto * theta_R && tp.theta <= R.osave[3];
+        bool leave = tp.finite && tp.theta <= o.kappa_resto * R.osave[11] && tp.theta <= R.osave[3];
         if (leave)
           leave = filter_ok_in(tp.theta, tp.f + R.osave[0] * tp.barB, R.osave[6], R.osave[7], (int)R.osave[8]);
         if (leave) {
@@ -1683,7 +1679,7 @@ struct WarpSolver {
         }
         R.s[r] = snew;
         R.rd[r] = tp_rd[r];
-        if (in_resto()) R.yd[r] = wq * tp_rd[r];
+        if (in_resto()) R.yd[r] = o.resto_weight * tp_rd[r];
       }
       last_alpha = astep;
       it++;

@@ -57,7 +57,7 @@ DEFAULT_OPTIONS = dict(
     # restoration: True = the kernels' feasibility-restoration phase (quadratic penalty over the same (x, s),
     # DESIGN.md section 3), restated below; 'l1' / 'quad' = the studies of oracle/restoration.py (IPOPT's l1
     # formulation / the penalty variant as a nested NLP), which the kernels do not mirror
-    restoration=False, resto_weight=1.0, kappa_resto=0.9, resto_max_iter=200, resto_relax_eq=True, resto_quad_weight=1.0,
+    restoration=False, resto_weight=1.0, kappa_resto=0.9, resto_max_iter=100, resto_relax_eq=True, resto_quad_weight=1.0,
 )
 
 
