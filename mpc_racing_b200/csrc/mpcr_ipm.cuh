@@ -1197,7 +1197,7 @@ struct WarpSolver {
     // ---- phase-loop state ------------------------------------------------------------
     int phase = kPhInit;
     int status = kMaxIterExceeded;
-    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0;
+    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0, ls_fail_mode = 0;
     bool cur_finite = true, soc_done = false, f_type = false;
     double theta_max = 0.0, theta_min = 0.0, mu_floor = 0.0;
     double dw = 0.0, dw_last = 0.0, last_alpha = 0.0, last_dw = 0.0;
@@ -1354,6 +1354,10 @@ struct WarpSolver {
               } else {
                 acc_count = 0;
               }
+              // IPOPT does not start the restoration phase at an almost feasible point: a failed line
+              // search there restores the stored acceptable point (here: only when that is this
+              // iterate) or ends "Restoration Failed" (IpBacktrackingLineSearch.cpp).
+              ls_fail_mode = (!in_resto() && e.pr_inf <= 1e-2 * o.tol) ? (acc_count > 0 ? 1 : 2) : 0;
               if (!done && it >= o.max_iter) { status = kMaxIterExceeded; done = true; }
             }
             // monotone barrier update (Waechter & Biegler eq. (7)); may fire repeatedly
@@ -1463,8 +1467,8 @@ struct WarpSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
           } else {
@@ -1581,8 +1585,8 @@ struct WarpSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
           } else {
@@ -1618,8 +1622,8 @@ struct WarpSolver {
         alpha *= o.alpha_red_factor;
         phase = kPhBacktrack;
         if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
         continue;

@@ -1292,7 +1292,7 @@ struct LaneSolver {
 
     int phase = kPhInit;
     int status = kMaxIterExceeded;
-    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0;
+    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0, ls_fail_mode = 0;
     bool cur_finite = true, soc_done = false, f_type = false;
     double theta_max = 0.0, theta_min = 0.0, mu_floor = 0.0;
     double dw = 0.0, dw_last = 0.0, last_alpha = 0.0, last_dw = 0.0;
@@ -1457,6 +1457,8 @@ struct LaneSolver {
             } else {
               acc_count = 0;
             }
+            // almost feasible: no restoration phase; the acceptable point (this iterate) or failure
+            ls_fail_mode = (!resto && e.pr_inf <= 1e-2 * o.tol) ? (acc_count > 0 ? 1 : 2) : 0;
             if (!done && it >= o.max_iter) { status = kMaxIterExceeded; done = true; }
           }
           while (!done && e.E(mu) <= o.barrier_tol_factor * mu && mu > mu_floor) {
@@ -1575,8 +1577,8 @@ struct LaneSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (o.restoration && !resto) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (o.restoration && !resto && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
           } else {
@@ -1663,8 +1665,8 @@ struct LaneSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (o.restoration && !resto) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (o.restoration && !resto && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
           } else {
@@ -1700,8 +1702,8 @@ struct LaneSolver {
         alpha *= o.alpha_red_factor;
         phase = kPhBacktrack;
         if (!(alpha >= amin && n_ls < 60)) {
-              if (o.restoration && !resto) { want_resto = true; continue; }
-              status = kRestorationNeeded;
+              if (o.restoration && !resto && ls_fail_mode == 0) { want_resto = true; continue; }
+              status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
         continue;

@@ -339,6 +339,15 @@ def solve(nlp, options=None, trace=None, stop=None):
                 break
         else:
             acceptable_count = 0
+        # What a failed line search does at THIS iterate (IpBacktrackingLineSearch.cpp, the block
+        # before PerformRestoration): at an almost feasible point (scaled violation <= 1e-2 tol) the
+        # restoration phase is not started; the stored acceptable point is restored ("Solved To
+        # Acceptable Level") or, with none, the run ends "Restoration Failed".  The stored point is
+        # the latest iterate that passed the acceptable test; only the case "that is the current
+        # iterate" (acceptable_count > 0) is followed here, an older stored point is not kept.
+        ls_fail_mode = 0
+        if not resto and pr_inf <= 1e-2 * o['tol']:
+            ls_fail_mode = 1 if acceptable_count > 0 else 2
         if it >= o['max_iter']:
             status = MAXITER_EXCEEDED
             break
@@ -527,6 +536,12 @@ def solve(nlp, options=None, trace=None, stop=None):
                     break
             alpha *= o['alpha_red_factor']
         ls_total += n_ls
+        if not accepted and ls_fail_mode == 1:
+            status = SOLVED_TO_ACCEPTABLE_LEVEL
+            break
+        if not accepted and ls_fail_mode == 2:
+            status = RESTORATION_NEEDED
+            break
         if not accepted and o['restoration'] is True and not resto:
             # ---- enter the restoration phase at the current iterate (x_R, s_R): the kernels' text ------
             theta_R = theta
