@@ -317,7 +317,7 @@ def run_gpu(args):
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * max(1, dsolver.launch_info()["kernels_per_solve"]),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": "measured here: DFMA-chain microbenchmark (mpcr_fp64_peak_tflops)",

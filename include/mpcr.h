@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MPCR_VERSION 102
+#define MPCR_VERSION 103
 
 /* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
  * models/BlendedBicycleModel.py:23-46 blend of the two) */
@@ -50,6 +50,11 @@ extern "C" {
 /* integrators of the NLP's dynamics rows (also used by mpcr_model_eval) */
 #define MPCR_INTEGRATOR_EULER 0
 #define MPCR_INTEGRATOR_RK4 1
+
+/* dispatch order of the problems of a batch (mpcr_config.schedule) */
+#define MPCR_SCHEDULE_AUTO 0       /* curvature-first when the batch exceeds one wave, else index order */
+#define MPCR_SCHEDULE_INDEX 1      /* problems in index order */
+#define MPCR_SCHEDULE_CURVATURE 2  /* always expected-longest-first */
 
 /* per-problem status codes */
 #define MPCR_SOLVE_SUCCEEDED 0
@@ -95,7 +100,10 @@ typedef struct mpcr_config {
                               * (IPOPT would; quadratic-penalty variant) instead of returning
                               * MPCR_RESTORATION_FAILED.  Selects the kernel build that contains the phase
                               * (~6 % slower per iteration).  0 = off (default) */
-  int32_t reserved_;
+  int32_t schedule;          /* MPCR_SCHEDULE_*: order in which the persistent warps pick problems off the batch.
+                              * Results do not depend on it; kernel time does (stragglers picked last leave
+                              * the GPU idle).  0 = auto: expected-longest-first (reference-path curvature)
+                              * for batches larger than one wave of resident warps */
 } mpcr_config;
 
 typedef struct mpcr_handle mpcr_handle;
@@ -145,6 +153,9 @@ int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
 /* Launch geometry of the last solve launch (or of the warp kernel before any launch):
  * blocks, warps per block, dynamic shared bytes. */
 int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem_bytes);
+/* Number of this library's kernels the last solve call launched (1 solve kernel, + 2 schedule
+ * kernels when the batch was reordered, mpcr_config.schedule). */
+int mpcr_last_launch_count(mpcr_handle* h, int* kernels);
 
 /* ---- track geometry (replaces splines/ParameterizedLine.py:19-105 and
  * splines/ParameterizedCenterline.py:61-91 for batches of queries) -----------------------

@@ -31,7 +31,7 @@ class MpcrConfig(C.Structure):
         ("dual_inf_tol", C.c_double), ("constr_viol_tol", C.c_double),
         ("compl_inf_tol", C.c_double), ("mu_init", C.c_double),
         ("solve_kernel", C.c_int32), ("integrator", C.c_int32),
-        ("restoration", C.c_int32), ("reserved_", C.c_int32),
+        ("restoration", C.c_int32), ("schedule", C.c_int32),
     ]
 
 
@@ -43,7 +43,7 @@ SOLVE_ARGTYPES = [C.c_void_p] * 8 + [C.c_void_p] * 9   # 8 inputs, 9 outputs (ra
 EXPORTED_SYMBOLS = [
     "mpcr_version", "mpcr_config_default", "mpcr_create", "mpcr_destroy", "mpcr_last_error",
     "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
-    "mpcr_launch_info", "mpcr_fp64_peak_tflops",
+    "mpcr_launch_info", "mpcr_last_launch_count", "mpcr_fp64_peak_tflops",
     "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
     "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step", "mpcr_model_eval",
 ]
@@ -85,6 +85,8 @@ def load_library(path=None):
     lib.mpcr_last_kernel_ms.restype = C.c_int
     lib.mpcr_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpcr_launch_info.restype = C.c_int
+    lib.mpcr_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.mpcr_last_launch_count.restype = C.c_int
     lib.mpcr_fp64_peak_tflops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.mpcr_fp64_peak_tflops.restype = C.c_int
     V = C.c_void_p

@@ -43,7 +43,7 @@ inline void config_default(mpcr_config* c) {
   c->solve_kernel = MPCR_KERNEL_AUTO;
   c->integrator = MPCR_INTEGRATOR_EULER;
   c->restoration = 0;
-  c->reserved_ = 0;
+  c->schedule = MPCR_SCHEDULE_AUTO;
 }
 
 inline void config_convert(const mpcr_config& c, Config* out) {
@@ -132,6 +132,7 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.solve_kernel < 0 || c.solve_kernel > 2) { *why = "unknown solve_kernel"; return false; }
   if (c.integrator < 0 || c.integrator > 1) { *why = "unknown integrator"; return false; }
   if (c.restoration < 0 || c.restoration > 1) { *why = "restoration must be 0 or 1"; return false; }
+  if (c.schedule < 0 || c.schedule > 2) { *why = "unknown schedule"; return false; }
   if (c.integrator == MPCR_INTEGRATOR_RK4 && c.solve_kernel == MPCR_KERNEL_WARP) {
     *why = "the RK4 integrator is implemented by the lane kernel only";
     return false;

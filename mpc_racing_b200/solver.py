@@ -51,7 +51,7 @@ class BatchedMPC:
                  runtime_params: Optional[RuntimeControllerParameters] = None,
                  wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
                  tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False,
-                 solve_kernel=0, integrator="euler", restoration=False):
+                 solve_kernel=0, integrator="euler", restoration=False, schedule="auto"):
         self.lib = _capi.load_library()
         fp = fixed_params or FixedControllerParameters()
         rp = runtime_params or RuntimeControllerParameters()
@@ -80,7 +80,9 @@ class BatchedMPC:
         cfg.solve_kernel = int({"auto": 0, "warp": 1, "lanes": 2}.get(solve_kernel, solve_kernel))
         # "euler" = the reference's discretisation; "rk4" = extension, solved by the lane kernel
         cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
-        cfg.restoration = int(bool(restoration))     # feasibility restoration (lane kernel), off = reference-free status -2
+        cfg.restoration = int(bool(restoration))     # feasibility restoration phase; off = status -2 instead
+        # dispatch order of the batch: "auto" = expected-longest-first for batches above one wave
+        cfg.schedule = int({"auto": 0, "index": 1, "curvature": 2}.get(schedule, schedule))
         self.cfg = cfg
         self.N = cfg.N
         self.on_device = bool(on_device)
@@ -109,7 +111,9 @@ class BatchedMPC:
     def launch_info(self):
         b, w, s = C.c_int(), C.c_int(), C.c_int()
         self.lib.mpcr_launch_info(self._h, C.byref(b), C.byref(w), C.byref(s))
-        return dict(blocks=b.value, warps_per_block=w.value, smem_bytes=s.value)
+        n = C.c_int()
+        self.lib.mpcr_last_launch_count(self._h, C.byref(n))
+        return dict(blocks=b.value, warps_per_block=w.value, smem_bytes=s.value, kernels_per_solve=n.value)
 
     def fp64_peak_tflops(self):
         v = C.c_double()

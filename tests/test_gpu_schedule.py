@@ -1,0 +1,46 @@
+"""mpcr_config.schedule: the dispatch order of a batch (expected-longest-first by reference-path
+curvature) changes kernel time only - every output of every problem is bit-identical to the
+index-order run, i.e. the order is a permutation and the solve does not depend on it."""
+import numpy as np
+import pytest
+
+from mpc_racing_b200.workload import load_fixture, make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_schedule_changes_nothing_but_the_order():
+    from mpc_racing_b200.solver import BatchedMPC
+    b = make_batch(3000)                                     # > one wave of resident warps (1036 on B200)
+    args = (b["x0"], b["u_prev"], b["s0"], b["cx"], b["cy"])
+    ref = BatchedMPC(N=30, Ts=0.05, schedule="index").solve(*args)
+    for sched in ("auto", "curvature"):
+        s = BatchedMPC(N=30, Ts=0.05, schedule=sched)
+        r = s.solve(*args)
+        assert s.launch_info()["kernels_per_solve"] == 3
+        for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters"):
+            assert np.array_equal(getattr(r, k), getattr(ref, k), equal_nan=True), (sched, k)
+    # a batch of one wave or less is not reordered under "auto"
+    s = BatchedMPC(N=30, Ts=0.05)
+    r = s.solve(*[a[:64] for a in args])
+    assert s.launch_info()["kernels_per_solve"] == 1
+    assert np.array_equal(r.U, ref.U[:64])
+
+
+def test_schedule_with_degenerate_inputs():
+    """NaN / zero polynomials (no curvature defined) must still give a permutation: every problem
+    gets a status, the good ones their usual result."""
+    from mpc_racing_b200.solver import BatchedMPC
+    d = load_fixture("cfg2_shanghai_4096.npz")
+    n = 1500
+    x0, up, s0, cx, cy = (d[k][:n].copy() for k in ("x0", "u_prev", "s0", "cx", "cy"))
+    cx[5] = np.nan
+    cy[6] = 0.0
+    cx[6] = 0.0
+    x0[7, 3] = np.inf
+    ref = BatchedMPC(N=30, Ts=0.05, schedule="index").solve(x0, up, s0, cx, cy)
+    r = BatchedMPC(N=30, Ts=0.05, schedule="curvature").solve(x0, up, s0, cx, cy)
+    assert np.array_equal(r.status, ref.status)
+    ok = ref.status >= 0
+    assert ok.sum() >= n - 10
+    assert np.array_equal(r.U[ok], ref.U[ok])
