@@ -90,7 +90,9 @@ constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
 constexpr int kPS = 10;         // row stride of the 9x9 cost-to-go matrix (even: aligned rows)
 
 constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
-constexpr int kScrP = 0, kScrT = 90, kScrG = 198, kScrPv = 342, kScrTv = 370, kScrGv = 398, kScrMisc = 434;
+constexpr int kTS = 18;         // row stride of T [9][15 used]: even (aligned rows), 9 row writers on distinct banks
+constexpr int kGS = 16;         // row stride of G [12][15 used]
+constexpr int kScrT = 0, kScrG = 9 * kTS, kScrMisc = kScrG + 12 * kGS;   // T and G contiguous (kkt_solve scratch)
 constexpr int kScratch = kScrMisc + kMisc;
 MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
 MPCR_HD int stage_doubles(int N) { return (N + 1) * kStride; }
@@ -103,7 +105,8 @@ template <bool SG>
 struct WarpWs {
   double* base_;   // host build (emulation): start of the workspace; unused on the device
   double* stage_;  // SG only: global slab
-  int soff_;       // offset of the scratch area inside the shared/host workspace
+  int shalf_;      // HALF the offset of the scratch area inside the shared/host workspace: written as
+                   // 2 * shalf_ the compiler sees a 16-byte aligned scratch base (vector LDS/STS)
   MPCR_D double* sm() const {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) double mpcr_dyn_smem[];
@@ -115,15 +118,11 @@ struct WarpWs {
   MPCR_HD void bind(double* base, double* stage_base, int N) {
     base_ = base;
     stage_ = stage_base;
-    soff_ = SG ? 0 : (N + 1) * kStride;
+    shalf_ = SG ? 0 : (N + 1) * (kStride / 2);
   }
-  MPCR_D double* P() const { return sm() + soff_ + kScrP; }    // [9][kPS]
-  MPCR_D double* T() const { return sm() + soff_ + kScrT; }       // [9][12]
-  MPCR_D double* G() const { return sm() + soff_ + kScrG; }      // [12][12]
-  MPCR_D double* pv() const { return sm() + soff_ + kScrPv; }     // [3][9]
-  MPCR_D double* tv() const { return sm() + soff_ + kScrTv; }     // [3][9]
-  MPCR_D double* gv() const { return sm() + soff_ + kScrGv; }     // [3][12]
-  MPCR_D double* misc() const { return sm() + soff_ + kScrMisc; }   // [kMisc]
+  MPCR_D double* T() const { return sm() + 2 * shalf_ + kScrT; }       // [9][kTS]
+  MPCR_D double* G() const { return sm() + 2 * shalf_ + kScrG; }       // [12][kGS]
+  MPCR_D double* misc() const { return sm() + 2 * shalf_ + kScrMisc; }   // [kMisc]
   MPCR_D double* st(int k) const { return (SG ? stage_ : sm()) + k * kStride; }   // [(N+1)][kStride]
 };
 
@@ -276,7 +275,10 @@ struct WarpSolver {
     colslot_lo = 0ull;
     colslot_hi = 0u;
     for (int r = 0; r < 12; ++r) {
-      const unsigned long long v = (lane < 12) ? (unsigned long long)(slot_of(r, lane) & 0xff) : kZeroSlot;
+      // lanes 0-11: column `lane` of the stage Hessian; lane 12: the stage gradient (right-hand
+      // side 0, stored right behind the Hessian slots); lanes 13, 14 (wrap vectors): zero
+      const unsigned long long v = (lane < 12) ? (unsigned long long)(slot_of(r, lane) & 0xff)
+                                   : (lane == 12 ? (unsigned long long)(kOffGs - kOffHs + r) : kZeroSlot);
       if (r < 8) colslot_lo |= v << (8 * r);
       else colslot_hi |= (unsigned)v << (8 * (r - 8));
     }
@@ -710,23 +712,29 @@ struct WarpSolver {
 
   MPCR_D bool riccati(double dw) {
     const double Ts = cfg.Ts;
-    double* P = ws.P();
-    double* T = ws.T();
-    double* G = ws.G();
+    double* T = ws.T();   // [9][kTS]:  columns 0-11 = P M,           12-14 = t_j = p_j + P b_j
+    double* G = ws.G();   // [12][kGS]: columns 0-11 = M' P M + H,     12-14 = g_j = grad_j + M' t_j
     const int nrhs = cfg.wrap ? kRhs : 1;
+    // Lane c < 9 carries column c of the cost-to-go matrix P (= its row c: P is symmetric) and
+    // entry c of the three cost-to-go vectors in REGISTERS from one stage to the next, so a stage
+    // costs two shared-memory round trips (T, G) instead of three.
+    double pr[9], pj[kRhs];
     {
       const double* stN = ws.st(N);
+      double* P0 = G;       // staging of the terminal matrix, stride kPS (G is free until round 2)
       for (int j = 0; j < 3; ++j) {
         int e = lane + 32 * j;
         if (e < 81) {
           int r = e / 9, c = e % 9;
-          P[r * kPS + c] = stage_entry(stN, slot_of(r, c), dw);
+          P0[r * kPS + c] = stage_entry(stN, slot_of(r, c), dw);
         }
       }
-      if (lane < 27) {
-        int j = lane / 9, a = lane % 9;
-        ws.pv()[lane] = (j == 0) ? stN[kOffGs + a] : 0.0;
-      }
+      syncwarp();
+      const int c = lane < 9 ? lane : 0;
+      for (int a = 0; a < 9; ++a) pr[a] = P0[a * kPS + c];
+      pj[0] = stN[kOffGs + c];
+      pj[1] = 0.0;
+      pj[2] = 0.0;
     }
     syncwarp();
     bool ok = true;
@@ -734,52 +742,41 @@ struct WarpSolver {
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
       double* st = ws.st(k);
-      // ---- round 1: T = P M (rows), t_j = p_j + P b_j -----------------------------
+      // ---- round 1: row `lane` of T = P M, and t_j ---------------------------------------
       if (lane < 9) {
-        double pr[9], A[21], out[12];
-        for (int c = 0; c < 9; ++c) pr[c] = P[lane * kPS + c];
+        double A[21], out[12];
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(pr, A, Ts, out);
-        for (int c = 0; c < 12; ++c) T[lane * 12 + c] = out[c];
-        double t0 = ws.pv()[lane];
+        for (int c = 0; c < 12; ++c) T[lane * kTS + c] = out[c];
+        double t0 = pj[0];
         for (int c = 0; c < 6; ++c) t0 += pr[c] * st[kOffB + c];
-        ws.tv()[lane] = t0;
-        ws.tv()[9 + lane] = ws.pv()[9 + lane];
-        ws.tv()[18 + lane] = ws.pv()[18 + lane];
+        T[lane * kTS + 12] = t0;
+        T[lane * kTS + 13] = pj[1];
+        T[lane * kTS + 14] = pj[2];
       }
       syncwarp();
-      // ---- round 2: G[:, c] = M' T[:, c] + stage Hessian column ; g_j = grad_j + M' t_j
+      // ---- round 2: column `lane` of G = M' T + (stage Hessian | gradient | wrap vector) -----
       if (lane < 12 + nrhs) {
-        const bool isvec = lane >= 12;
-        const int j = lane - 12;
         double tc[9], A[21], out[12];
-        for (int r = 0; r < 9; ++r) tc[r] = isvec ? ws.tv()[j * 9 + r] : T[r * 12 + lane];
+        for (int r = 0; r < 9; ++r) tc[r] = T[r * kTS + lane];
         for (int c = 0; c < 21; ++c) A[c] = st[kOffA + c];
         mulM(tc, A, Ts, out);
-        if (!isvec) {
 #pragma unroll
-          for (int r = 0; r < 12; ++r) {
-            const int slot = (r < 8) ? (int)((colslot_lo >> (8 * r)) & 0xff) : (int)((colslot_hi >> (8 * (r - 8))) & 0xff);
-            G[r * 12 + lane] = out[r] + st[kOffHs + slot];
-          }
-          G[lane * 12 + lane] += dwc;
-        } else {
-#pragma unroll
-          for (int r = 0; r < 12; ++r) {
-            double g = out[r];
-            if (j == 0) g += st[kOffGs + r];
-            ws.gv()[j * 12 + r] = g;
-          }
-          if (j >= 1) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
-            double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
-            ws.gv()[j * 12 + 9 + (j - 1)] += a;
-          }
+        for (int r = 0; r < 12; ++r) {
+          const int slot = (r < 8) ? (int)((colslot_lo >> (8 * r)) & 0xff) : (int)((colslot_hi >> (8 * (r - 8))) & 0xff);
+          G[r * kGS + lane] = out[r] + st[kOffHs + slot];
+        }
+        if (lane < 12) {
+          G[lane * kGS + lane] += dwc;
+        } else if (lane > 12) {   // wrap vector: +1 on u_0, -1 on u_{N-1}
+          const double a = (k == 0 ? 1.0 : 0.0) - (k == N - 1 ? 1.0 : 0.0);
+          G[(9 + (lane - 13)) * kGS + lane] += a;
         }
       }
       syncwarp();
-      // ---- round 3: LDL' of H_ww (every lane), gains, cost-to-go update ------------
-      const double h00 = G[9 * 12 + 9], h10 = G[10 * 12 + 9], h20 = G[11 * 12 + 9];
-      const double h11 = G[10 * 12 + 10], h21 = G[11 * 12 + 10], h22 = G[11 * 12 + 11];
+      // ---- round 3: LDL' of H_ww (every lane), gains, cost-to-go update in registers -------
+      const double h00 = G[9 * kGS + 9], h10 = G[10 * kGS + 9], h20 = G[11 * kGS + 9];
+      const double h11 = G[10 * kGS + 10], h21 = G[11 * kGS + 10], h22 = G[11 * kGS + 11];
       const double d0 = h00;
       const double id0 = 1.0 / d0;
       const double l10 = h10 * id0, l20 = h20 * id0;
@@ -791,33 +788,44 @@ struct WarpSolver {
       const double id2 = 1.0 / d2;
       // identical in every lane (same inputs, same arithmetic) -> uniform branch
       if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) { ok = false; break; }
-      if (lane < 9 || (lane >= 12 && lane < 12 + nrhs)) {
-        const bool isvec = lane >= 12;
+      if (lane < 9) {
         const int c = lane;
-        const int j = lane - 12;
-        const double* src = isvec ? (ws.gv() + j * 12) : (G + c);
-        const int sstride = isvec ? 1 : 12;
-        const double r0 = src[9 * sstride], r1 = src[10 * sstride], r2 = src[11 * sstride];
-        const double f0 = r0, f1 = r1 - l10 * f0, f2 = r2 - l20 * f0 - l21 * f1;
-        const double z2 = f2 * id2;
-        const double z1 = f1 * id1 - l21 * z2;
-        const double z0 = f0 * id0 - l10 * z1 - l20 * z2;
-        const double k0 = -z0, k1 = -z1, k2 = -z2;
-        double* kdst = isvec ? (st + kOffKf + j * 3) : (st + kOffK + c);
-        const int kstride = isvec ? 1 : 9;
-        kdst[0] = k0;
-        kdst[kstride] = k1;
-        kdst[2 * kstride] = k2;
-        double* pdst = isvec ? (ws.pv() + j * 9) : (P + c);
-        const int pstride = isvec ? 1 : kPS;
+        // rows 9-11 of column c (= entries c of rows 9-11: G is symmetric up to round-off)
+        const double r0 = G[9 * kGS + c], r1 = G[10 * kGS + c], r2 = G[11 * kGS + c];
+        {
+          const double f1 = r1 - l10 * r0, f2 = r2 - l20 * r0 - l21 * f1;
+          const double z2 = f2 * id2;
+          const double z1 = f1 * id1 - l21 * z2;
+          const double z0 = r0 * id0 - l10 * z1 - l20 * z2;
+          st[kOffK + c] = -z0;
+          st[kOffK + 9 + c] = -z1;
+          st[kOffK + 18 + c] = -z2;
 #pragma unroll
-        for (int a = 0; a < 9; ++a)
-          pdst[a * pstride] = src[a * sstride] + G[9 * 12 + a] * k0 + G[10 * 12 + a] * k1 +
-                              G[11 * 12 + a] * k2;
+          for (int a = 0; a < 9; ++a)
+            pr[a] = G[a * kGS + c] - G[9 * kGS + a] * z0 - G[10 * kGS + a] * z1 - G[11 * kGS + a] * z2;
+        }
+#pragma unroll
+        for (int j = 0; j < kRhs; ++j) {
+          if (j < nrhs) {
+            const double g0 = G[9 * kGS + 12 + j], g1 = G[10 * kGS + 12 + j], g2 = G[11 * kGS + 12 + j];
+            const double f1 = g1 - l10 * g0, f2 = g2 - l20 * g0 - l21 * f1;
+            const double z2 = f2 * id2;
+            const double z1 = f1 * id1 - l21 * z2;
+            const double z0 = g0 * id0 - l10 * z1 - l20 * z2;
+            if (c == j) {
+              st[kOffKf + j * 3] = -z0;
+              st[kOffKf + j * 3 + 1] = -z1;
+              st[kOffKf + j * 3 + 2] = -z2;
+            }
+            pj[j] = G[c * kGS + 12 + j] - r0 * z0 - r1 * z1 - r2 * z2;
+          }
+        }
       }
-      syncwarp();
+      // no barrier here: round 1 of the next stage reads registers and writes T, whose last
+      // readers (round 2) are behind the barrier above
     }
     if (!ok) return false;
+    syncwarp();
     // ---- forward sweep: lane groups 0-10 / 11-21 / 22-31 each roll out ONE right-hand side;
     //      the group leaders park (z_{k+1}, w_k) in stage k's (now dead) gain slot -----------
     const int grp = (nrhs == 1) ? 0 : (lane < 11 ? 0 : (lane < 22 ? 1 : 2));
@@ -905,7 +913,7 @@ struct WarpSolver {
       double t = shfl(dsh, prev_lane());
       dzp[6] = (lane == 0) ? 0.0 : t;
     }
-    double* loc = ws.T();   // scratch [(N+1)][7]: T (108) + G (144) are contiguous
+    double* loc = ws.T();   // scratch [(N+1)][7]: T (162) + G (192) are contiguous
     if (act) {
       const double* st = ws.st(lane);
       const double v12[12] = {dzp[0], dzp[1], dzp[2], dzp[3], dzp[4], dzp[5], dzp[6], 0, 0,
