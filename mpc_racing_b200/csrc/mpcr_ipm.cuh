@@ -393,11 +393,15 @@ struct WarpSolver {
         th += fabs(dcs[k] * t.c[k]);
       }
     }
+    RowRegs nx{};
+    row_fetch(0, nx);
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
+      const RowRegs c = nx;
+      row_fetch(r + 1, nx);
       double rdv = 0.0;
       if (on(r)) {
-        const double sv = R.s[r] + at * R.dsr[r];
+        const double sv = c.s + at * c.dsr;
         rdv = row_value(r, t.u, up, t.sh, shp, sc.eC) - sv;
         if (inner) fl += 0.5 * o.resto_weight * rdv * rdv;
         else th += fabs(rdv);
@@ -542,19 +546,34 @@ struct WarpSolver {
   // -------------------------------------------------------------------------
   double Dw[2];   // D of the two wrap rows (uniform, from lane 0)
 
+  // The row arrays live in local memory and mostly miss L1 (shared memory takes the carve-out), and
+  // the row loops are not unrolled: every iteration would wait a full L2 round trip for its own
+  // loads.  The loops therefore fetch row r + 1 into registers while row r is being processed.
+  struct RowRegs { double s, yd, vL, vU, rd, dsr; };
+  MPCR_D void row_fetch(int r, RowRegs& q) const {
+    if (r < kNumRows && on(r)) {
+      q.s = R.s[r];
+      q.yd = R.yd[r];
+      q.rd = R.rd[r];
+      q.dsr = R.dsr[r];
+      if (row_hasL(r)) q.vL = R.vL[r];
+      if (row_hasU(r)) q.vU = R.vU[r];
+    }
+  }
+
   // Sigma_r and d(barrier objective)/d(slack r)
-  MPCR_D void sigma_gsb(int r, double& sg, double& g) const {
+  MPCR_D void sigma_gsb(int r, const RowRegs& c, double& sg, double& g) const {
     sg = 0.0;
     g = 0.0;
     if (row_hasL(r)) {
-      const double isl = 1.0 / (R.s[r] - lo(r));
-      sg += R.vL[r] * isl;
+      const double isl = 1.0 / (c.s - lo(r));
+      sg += c.vL * isl;
       g -= mu * isl;
       if (!row_hasU(r)) g += o.kappa_d * mu;
     }
     if (row_hasU(r)) {
-      const double isu = 1.0 / (hi(r) - R.s[r]);
-      sg += R.vU[r] * isu;
+      const double isu = 1.0 / (hi(r) - c.s);
+      sg += c.vU * isu;
       g += mu * isu;
       if (!row_hasL(r)) g -= o.kappa_d * mu;
     }
@@ -567,15 +586,22 @@ struct WarpSolver {
     double Rtt = 0.0, Rss = 0.0, eth = 0.0, est = 0.0;     // rows acting on (thr_k, st_k) alone
     double Dthr = 0.0, ethr = 0.0, Dst = 0.0, esr = 0.0;   // rate rows (kDThr, kDSt)
     double Dprog = 0.0, eprog = 0.0, Dlane = 0.0, elane = 0.0;
+    RowRegs nx{};
+    row_fetch(0, nx);
+    double nrdv = (rdv && on(0)) ? rdv[0] : 0.0;
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
+      const RowRegs c = nx;
+      const double crdv = nrdv;
+      row_fetch(r + 1, nx);
+      if (rdv && r + 1 < kNumRows && on(r + 1)) nrdv = rdv[r + 1];
       double Dr = 0.0, er = 0.0;
       if (on(r)) {
         if (mode == 0) {
           double sg, g;
-          sigma_gsb(r, sg, g);
+          sigma_gsb(r, c, sg, g);
           Dr = sg + dw;
-          er = Dr * (rdv ? rdv[r] : 0.0) + g;
+          er = Dr * (rdv ? crdv : 0.0) + g;
           if (in_resto()) {
             // row in the objective: min over ds of wq/2 (J dx - ds + rd)^2 + Sigma/2 ds^2 + g ds
             const double kap = o.resto_weight / (o.resto_weight + Dr);
@@ -584,7 +610,7 @@ struct WarpSolver {
           }
         } else {
           Dr = 1.0;
-          er = -((row_hasU(r) ? R.vU[r] : 0.0) - (row_hasL(r) ? R.vL[r] : 0.0));
+          er = -((row_hasU(r) ? c.vU : 0.0) - (row_hasL(r) ? c.vL : 0.0));
         }
       }
       switch (r) {
@@ -1034,30 +1060,34 @@ struct WarpSolver {
         sum_y += fabs(lam[a] / dcs[a]);
       }
     }
+    RowRegs nx{};
+    row_fetch(0, nx);
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
+      const RowRegs c = nx;
+      row_fetch(r + 1, nx);
       if (!on(r)) continue;
-      double rs = -R.yd[r];
+      double rs = -c.yd;
       if (row_hasL(r)) {
-        rs -= R.vL[r];
-        const double pr_ = (R.s[r] - lo(r)) * R.vL[r];
+        rs -= c.vL;
+        const double pr_ = (c.s - lo(r)) * c.vL;
         pmax = fmax(pmax, pr_);
         pmin = fmin(pmin, pr_);
-        sum_v += fabs(R.vL[r]);
+        sum_v += fabs(c.vL);
       }
       if (row_hasU(r)) {
-        rs += R.vU[r];
-        const double pr_ = (hi(r) - R.s[r]) * R.vU[r];
+        rs += c.vU;
+        const double pr_ = (hi(r) - c.s) * c.vU;
         pmax = fmax(pmax, pr_);
         pmin = fmin(pmin, pr_);
-        sum_v += fabs(R.vU[r]);
+        sum_v += fabs(c.vU);
       }
       dinf = fmax(dinf, fabs(rs));
-      if (!in_resto()) prinf = fmax(prinf, fabs(R.rd[r]));   // restoration: the rows sit in the objective
-      sum_y += fabs(R.yd[r]);
+      if (!in_resto()) prinf = fmax(prinf, fabs(c.rd));   // restoration: the rows sit in the objective
+      sum_y += fabs(c.yd);
       double bl, bh;
       row_bounds(r, bl, bh);
-      double val = R.rd[r] + R.s[r];
+      double val = c.rd + c.s;
       if (r == kLane) val /= ddl;
       if (row_hasL(r)) vio = fmax(vio, bl - val);
       if (row_hasU(r)) vio = fmax(vio, val - bh);
@@ -1102,28 +1132,35 @@ struct WarpSolver {
     double a = 1.0, g = 0.0, th = 0.0;
     if (act)
       for (int k = 0; k < 6; ++k) th += fabs(dcs[k] * cres[k]);
+    RowRegs nx{};
+    row_fetch(0, nx);
+    double nrdv = (rdv && on(0)) ? rdv[0] : 0.0;
 #pragma unroll 1
     for (int r = 0; r < kNumRows; ++r) {
+      const RowRegs c = nx;
+      const double crdv = nrdv;
+      row_fetch(r + 1, nx);
+      if (rdv && r + 1 < kNumRows && on(r + 1)) nrdv = rdv[r + 1];
       double d = 0.0;
       if (on(r)) {
         const double jdx = row_lin(r, du, dup, dsh, dshp, dx);
-        d = jdx + (rdv ? rdv[r] : 0.0);
+        d = jdx + (rdv ? crdv : 0.0);
         if (in_resto()) {
           // slack step of a row that sits in the objective, and its share of grad(f_R)' d
           double sg, gb;
-          sigma_gsb(r, sg, gb);
+          sigma_gsb(r, c, sg, gb);
           d = (o.resto_weight * d - gb) / (o.resto_weight + sg + dwu);
-          g += o.resto_weight * R.rd[r] * (jdx - d);
+          g += o.resto_weight * c.rd * (jdx - d);
         } else {
-          th += fabs(R.rd[r]);
+          th += fabs(c.rd);
         }
         if (row_hasL(r)) {
-          const double sl = R.s[r] - lo(r);
+          const double sl = c.s - lo(r);
           if (d < 0.0) a = fmin(a, -tau * sl / d);
           g += (-mu / sl + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - R.s[r];
+          const double su = hi(r) - c.s;
           if (d > 0.0) a = fmin(a, tau * su / d);
           g += (mu / su - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
@@ -1641,22 +1678,26 @@ struct WarpSolver {
       const double astep = (phase == kPhSoc) ? a_soc : alpha;
       // dual steps: dyd = D ds + gsb - yd ; dv from the linearised complementarity
       double az = 1.0;
+      RowRegs nx{};
+      row_fetch(0, nx);
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
+        const RowRegs c = nx;
+        row_fetch(r + 1, nx);
         if (!on(r)) continue;
         double sg, gb;
-        sigma_gsb(r, sg, gb);
-        const double dyd = (sg + dw) * R.dsr[r] + gb - R.yd[r];
-        R.yd[r] += astep * dyd;
+        sigma_gsb(r, c, sg, gb);
+        const double dyd = (sg + dw) * c.dsr + gb - c.yd;
+        R.yd[r] = c.yd + astep * dyd;
         if (row_hasL(r)) {
-          const double sl = R.s[r] - lo(r);
-          const double a = mu / sl - R.vL[r] - R.vL[r] / sl * R.dsr[r];
-          if (a < 0.0) az = fmin(az, -tau * R.vL[r] / a);
+          const double sl = c.s - lo(r);
+          const double a = mu / sl - c.vL - c.vL / sl * c.dsr;
+          if (a < 0.0) az = fmin(az, -tau * c.vL / a);
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - R.s[r];
-          const double b = mu / su - R.vU[r] + R.vU[r] / su * R.dsr[r];
-          if (b < 0.0) az = fmin(az, -tau * R.vU[r] / b);
+          const double su = hi(r) - c.s;
+          const double b = mu / su - c.vU + c.vU / su * c.dsr;
+          if (b < 0.0) az = fmin(az, -tau * c.vU / b);
         }
       }
       az = warp_min(az);
@@ -1672,26 +1713,32 @@ struct WarpSolver {
       fval = tp.f;
       barB = tp.barB;
       cur_finite = tp.finite;
+      row_fetch(0, nx);
+      double ntrd = on(0) ? tp_rd[0] : 0.0;
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
+        const RowRegs c = nx;
+        const double ctrd = ntrd;
+        row_fetch(r + 1, nx);
+        if (r + 1 < kNumRows && on(r + 1)) ntrd = tp_rd[r + 1];
         if (!on(r)) continue;
-        const double sold = R.s[r];
-        const double snew = sold + astep * R.dsr[r];
+        const double sold = c.s;
+        const double snew = sold + astep * c.dsr;
         if (row_hasL(r)) {
           const double slo = sold - lo(r), sl = snew - lo(r);
-          const double dv = mu / slo - R.vL[r] - R.vL[r] / slo * R.dsr[r];
-          const double v = R.vL[r] + az * dv;
+          const double dv = mu / slo - c.vL - c.vL / slo * c.dsr;
+          const double v = c.vL + az * dv;
           R.vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
         }
         if (row_hasU(r)) {
           const double suo = hi(r) - sold, su = hi(r) - snew;
-          const double dv = mu / suo - R.vU[r] + R.vU[r] / suo * R.dsr[r];
-          const double v = R.vU[r] + az * dv;
+          const double dv = mu / suo - c.vU + c.vU / suo * c.dsr;
+          const double v = c.vU + az * dv;
           R.vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
         }
         R.s[r] = snew;
-        R.rd[r] = tp_rd[r];
-        if (in_resto()) R.yd[r] = o.resto_weight * tp_rd[r];
+        R.rd[r] = ctrd;
+        if (in_resto()) R.yd[r] = o.resto_weight * ctrd;
       }
       last_alpha = astep;
       it++;
