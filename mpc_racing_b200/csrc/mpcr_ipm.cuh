@@ -90,11 +90,11 @@ constexpr int kNz = 9, kNw = 3, kNzw = 12, kRhs = 3;
 constexpr int kPS = 10;         // row stride of the 9x9 cost-to-go matrix (even: aligned rows)
 
 constexpr int kMisc = 24;       // relaxed row bounds lo[10], hi[10] + spare
+constexpr int kPrmSlots = 20;   // >= sizeof(Params) / 8, even (static_assert below)
+constexpr int kPbSlots = 24;    // >= sizeof(ProblemView) / 8, even
 constexpr int kTS = 18;         // row stride of T [9][15 used]: even (aligned rows), 9 row writers on distinct banks
 constexpr int kGS = 16;         // row stride of G [12][15 used]
 constexpr int kScrT = 0, kScrG = 9 * kTS, kScrMisc = kScrG + 12 * kGS;   // T and G contiguous (kkt_solve scratch)
-constexpr int kScratch = kScrMisc + kMisc;
-MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
 MPCR_HD int stage_doubles(int N) { return (N + 1) * kStride; }
 
 // SG (stage-global): the per-stage storage lives in a global slab instead of shared memory.
@@ -123,6 +123,8 @@ struct WarpWs {
   MPCR_D double* T() const { return sm() + 2 * shalf_ + kScrT; }       // [9][kTS]
   MPCR_D double* G() const { return sm() + 2 * shalf_ + kScrG; }       // [12][kGS]
   MPCR_D double* misc() const { return sm() + 2 * shalf_ + kScrMisc; }   // [kMisc]
+  MPCR_D double* prm_mem() const { return sm() + 2 * shalf_ + kScrMisc + kMisc; }        // Params
+  MPCR_D double* pb_mem() const { return sm() + 2 * shalf_ + kScrMisc + kMisc + kPrmSlots; }   // ProblemView
   MPCR_D double* st(int k) const { return (SG ? stage_ : sm()) + k * kStride; }   // [(N+1)][kStride]
 };
 
@@ -200,6 +202,11 @@ struct ProblemView {     // uniform over the warp
   const double* u_warm;  // [2][N] or null
 };
 
+static_assert(sizeof(Params) <= kPrmSlots * sizeof(double), "kPrmSlots too small");
+static_assert(sizeof(ProblemView) <= kPbSlots * sizeof(double), "kPbSlots too small");
+constexpr int kScratch = kScrMisc + kMisc + kPrmSlots + kPbSlots;
+MPCR_HD int ws_doubles(int N) { return (N + 1) * kStride + kScratch; }
+
 struct SolveOut {        // pointers already offset to this problem
   double* U; double* X; double* S; double* eC; double* eL; double* lam_g;
   double* obj; int32_t* status; int32_t* iters; double* trace;
@@ -231,10 +238,12 @@ struct RowState {
 template <int MODEL, bool SG = false, bool RESTO = false>
 struct WarpSolver {
   const Config& cfg;
-  const Params& p;        // per-problem copy (GA sweeps override the runtime parameters)
   const IpmOptions& o;
-  const ProblemView& pb;
   WarpWs<SG> ws;
+  // per-problem parameters and inputs (uniform over the warp): ONE copy in shared memory, written
+  // by solve_problem, instead of 32 per-lane copies in local memory behind L2 latency
+  MPCR_D const Params& prm() const { return *reinterpret_cast<const Params*>(ws.prm_mem()); }
+  MPCR_D const ProblemView& pbv() const { return *reinterpret_cast<const ProblemView*>(ws.pb_mem()); }
   int lane, N;
   bool act;
   // primal iterate
@@ -265,9 +274,9 @@ struct WarpSolver {
   unsigned colslot_hi;
   double dwflag;            // 1 if diagonal entry (lane, lane) receives delta_w
 
-  MPCR_D WarpSolver(const Config& c, const Params& prm, const ProblemView& pv, RowState& rows,
+  MPCR_D WarpSolver(const Config& c, RowState& rows,
                     double* wsbase, double* stagebase)
-      : cfg(c), p(prm), o(c.o), pb(pv), R(rows) {
+      : cfg(c), o(c.o), R(rows) {
     lane = lane_id();
     N = c.N;
     act = lane < N;
@@ -295,14 +304,14 @@ struct WarpSolver {
   MPCR_D void row_bounds(int r, double& l, double& h) const {
     const double inf = 1.0e300;
     switch (r) {
-      case kThrUb: l = -inf; h = p.d_max; break;
-      case kThrLb: l = p.min_throttle; h = inf; break;
-      case kStUb: l = -inf; h = p.max_steer; break;
-      case kStLb: l = p.min_steer; h = inf; break;
-      case kDThr: case kDThr0: l = p.min_throttle_delta; h = p.max_throttle_delta; break;
-      case kDSt: case kDSt0: l = p.min_steer_delta; h = p.max_steer_delta; break;
-      case kProg: l = p.min_s_delta; h = cfg.Ts * p.v_max; break;
-      default: l = -pb.max_err; h = pb.max_err; break;
+      case kThrUb: l = -inf; h = prm().d_max; break;
+      case kThrLb: l = prm().min_throttle; h = inf; break;
+      case kStUb: l = -inf; h = prm().max_steer; break;
+      case kStLb: l = prm().min_steer; h = inf; break;
+      case kDThr: case kDThr0: l = prm().min_throttle_delta; h = prm().max_throttle_delta; break;
+      case kDSt: case kDSt0: l = prm().min_steer_delta; h = prm().max_steer_delta; break;
+      case kProg: l = prm().min_s_delta; h = cfg.Ts * prm().v_max; break;
+      default: l = -pbv().max_err; h = pbv().max_err; break;
     }
   }
 
@@ -315,8 +324,8 @@ struct WarpSolver {
       case kDThr: return uu[0] - up[0];
       case kDSt: return uu[1] - up[1];
       case kProg: return shh - shp;
-      case kDThr0: return uu[0] - pb.u_prev[0];
-      case kDSt0: return uu[1] - pb.u_prev[1];
+      case kDThr0: return uu[0] - pbv().u_prev[0];
+      case kDSt0: return uu[1] - pbv().u_prev[1];
       default: return ddl * eC;
     }
   }
@@ -339,10 +348,10 @@ struct WarpSolver {
     int src = prev_lane();
     for (int k = 0; k < 6; ++k) {
       double t = shfl(xx[k], src);
-      xp[k] = (lane == 0) ? pb.x0[k] : t;
+      xp[k] = (lane == 0) ? pbv().x0[k] : t;
     }
     double t = shfl(shh, src);
-    shp = (lane == 0) ? pb.s0 : t;
+    shp = (lane == 0) ? pbv().s0 : t;
     up[0] = shfl(uu[0], src);   // lane 0 receives u_{N-1} (wrap rows)
     up[1] = shfl(uu[1], src);
   }
@@ -366,7 +375,7 @@ struct WarpSolver {
     double f[6];
     f_model(MODEL, xp, t.u, cfg.Ts, f);
     StageCost sc;
-    stage_cost(p, pb.cx, pb.cy, t.x, t.sh, 0, sc);
+    stage_cost(prm(), pbv().cx, pbv().cy, t.x, t.sh, 0, sc);
     double fl = 0.0, th = 0.0;
     double prod = 1.0, lin = 0.0;       // barrier: -log(prod of slack distances) + kappa_d * lin
     bool fin = true;
@@ -374,10 +383,10 @@ struct WarpSolver {
     if (act) {
       if (!inner) {
         fl = sc.val;
-        if (lane == N - 1) fl -= p.lambda_s * t.sh;
+        if (lane == N - 1) fl -= prm().lambda_s * t.sh;
         if (lane >= 1) {
           double dsg = t.u[1] - up[1];
-          fl += p.beta_delta * dsg * dsg;
+          fl += prm().beta_delta * dsg * dsg;
         }
       } else {
         const double v9[9] = {t.x[0], t.x[1], t.x[2], t.x[3], t.x[4], t.x[5], t.sh, t.u[0], t.u[1]};
@@ -446,10 +455,10 @@ struct WarpSolver {
     for (int k = 0; k < 6; ++k) lz[k] = (mode == 0) ? lam[k] : 0.0;
     lin_model(MODEL, xp, u, cfg.Ts, lz, nullptr, lin, hm);
     StageCost sc;
-    stage_cost(p, pb.cx, pb.cy, x, sh, 2, sc);
+    stage_cost(prm(), pbv().cx, pbv().cy, x, sh, 2, sc);
     gcost[0] = df * sc.g3[0];
     gcost[1] = df * sc.g3[1];
-    gcost[2] = df * sc.g3[2] - ((lane == N - 1) ? df * p.lambda_s : 0.0);
+    gcost[2] = df * sc.g3[2] - ((lane == N - 1) ? df * prm().lambda_s : 0.0);
     gcost[3] = df * sc.gvx;
     gcost[4] = df * sc.gvy;
     for (int k = 0; k < 3; ++k) gC[k] = ddl * sc.gC[k];
@@ -651,7 +660,7 @@ struct WarpSolver {
     }
     if (!act) return;
     // steer-rate cost beta (sigma_k - sigma_{k-1})^2, k = 1..N-1 (control/MPC.py:97)
-    const double bsig = (lane >= 1 && !in_resto()) ? 2.0 * p.beta_delta * df : 0.0;
+    const double bsig = (lane >= 1 && !in_resto()) ? 2.0 * prm().beta_delta * df : 0.0;
     const double sgn = (mode == 0) ? 1.0 : -1.0;   // LSQ uses the negated gradient
     const double bq = (mode == 0) ? bsig : 0.0;
     double* st = ws.st(lane);
@@ -1047,7 +1056,7 @@ struct WarpSolver {
                    (on(kDThr0) ? R.yd[kDThr0] : 0.0) + (in_resto() ? R.pg[7] : 0.0);
       double ru1 = -out[10] + R.yd[kStUb] + R.yd[kStLb] + (on(kDSt) ? R.yd[kDSt] : 0.0) - ydst_n +
                    (on(kDSt0) ? R.yd[kDSt0] : 0.0) + (in_resto() ? R.pg[8] : 0.0) +
-                   2.0 * p.beta_delta * df * (sigc_prev - sig_n);
+                   2.0 * prm().beta_delta * df * (sigc_prev - sig_n);
       dinf = fmax(dinf, fmax(fabs(ru0), fabs(ru1)));
       if (lane == 0) {
         for (int a = 0; a < 6; ++a) dinf = fmax(dinf, fabs(y0[a] - out[a]));
@@ -1180,22 +1189,22 @@ struct WarpSolver {
     if (act) {
       rowmask = 0x4F;                                  // rows 0-3, 6
       if (lane > 0 || cfg.wrap) rowmask |= (1u << kDThr) | (1u << kDSt);
-      if (lane == 0 && pb.has_prev_thr) rowmask |= 1u << kDThr0;
-      if (lane == 0 && pb.has_prev_st) rowmask |= 1u << kDSt0;
+      if (lane == 0 && pbv().has_prev_thr) rowmask |= 1u << kDThr0;
+      if (lane == 0 && pbv().has_prev_st) rowmask |= 1u << kDSt0;
       if (cfg.lane_con) rowmask |= 1u << kLane;
     }
     // ---- initial guess (control/MPC.py:109-131) ----------------------------------
     {
-      double u0 = pb.u_prev[0], u1 = pb.u_prev[1];
-      if (pb.u_warm && act) {
+      double u0 = pbv().u_prev[0], u1 = pbv().u_prev[1];
+      if (pbv().u_warm && act) {
         int src = (lane + 1 < N) ? lane + 1 : N - 1;   // shift by one, repeat the last
-        u0 = pb.u_warm[src];
-        u1 = pb.u_warm[N + src];
+        u0 = pbv().u_warm[src];
+        u1 = pbv().u_warm[N + src];
       }
       u[0] = act ? u0 : 0.0;
       u[1] = act ? u1 : 0.0;
       double xr[6];
-      for (int k = 0; k < 6; ++k) { xr[k] = pb.x0[k]; x[k] = pb.x0[k]; }
+      for (int k = 0; k < 6; ++k) { xr[k] = pbv().x0[k]; x[k] = pbv().x0[k]; }
 #pragma unroll 1
       for (int k = 0; k < N; ++k) {
         double uk[2] = {shfl(u[0], k), shfl(u[1], k)};
@@ -1205,7 +1214,7 @@ struct WarpSolver {
         if (k == lane)
           for (int a = 0; a < 6; ++a) x[a] = fn[a];
       }
-      sh = act ? pb.s0 + (lane + 1) * cfg.Ts * p.v_max : pb.s0;
+      sh = act ? pbv().s0 + (lane + 1) * cfg.Ts * prm().v_max : pbv().s0;
     }
     for (int k = 0; k < 6; ++k) { lam[k] = 0.0; dcs[k] = 1.0; cres[k] = 0.0; dx[k] = 0.0; }
     for (int k = 0; k < 7; ++k) y0[k] = 0.0;
@@ -1329,7 +1338,7 @@ struct WarpSolver {
           double g = 0.0;
           if (act) {
             for (int k = 0; k < 5; ++k) g = fmax(g, fabs(gcost[k]));
-            g = fmax(g, fabs(2.0 * p.beta_delta * (sigc_prev - sig_n)));
+            g = fmax(g, fabs(2.0 * prm().beta_delta * (sigc_prev - sig_n)));
           }
           g = warp_max(g);
           if (g > o.nlp_scaling_max_gradient)
@@ -1483,7 +1492,7 @@ struct WarpSolver {
             } else if (act) {
               g += gcost[0] * dx[0] + gcost[1] * dx[1] + gcost[2] * dsh + gcost[3] * dx[3] +
                    gcost[4] * dx[4];
-              if (lane >= 1) g += 2.0 * p.beta_delta * df * sigc_prev * (du[1] - dup1);
+              if (lane >= 1) g += 2.0 * prm().beta_delta * df * sigc_prev * (du[1] - dup1);
             }
           }
           gpd = warp_sum(g);
@@ -1751,8 +1760,8 @@ struct WarpSolver {
       double xp[6], shp, up[2];
       gather_prev(x, sh, u, xp, shp, up);
       Poly4 px, py;
-      poly4_eval(pb.cx, shp, 1, px);
-      poly4_eval(pb.cy, shp, 1, py);
+      poly4_eval(pbv().cx, shp, 1, px);
+      poly4_eval(pbv().cy, shp, 1, py);
       const double dX = xp[0] - px.p, dY = xp[1] - py.p;
       if (act) {
         out.U[lane] = u[0];
@@ -1763,8 +1772,8 @@ struct WarpSolver {
         out.eL[lane] = -px.d1 * dX - py.d1 * dY;
       }
       if (lane == 0) {
-        for (int a = 0; a < 6; ++a) out.X[a * (N + 1)] = pb.x0[a];
-        out.S[0] = pb.s0;
+        for (int a = 0; a < 6; ++a) out.X[a * (N + 1)] = pbv().x0[a];
+        out.S[0] = pbv().s0;
         out.obj[0] = fval / df;
         out.status[0] = status;
         out.iters[0] = it;
@@ -1851,7 +1860,13 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     syncwarp();
   }
   RowState rows;
-  WarpSolver<MODEL, SG, RESTO> solver(cfg, prm, pv, rows, wsbase, stagebase);
+  WarpSolver<MODEL, SG, RESTO> solver(cfg, rows, wsbase, stagebase);
+  syncwarp();                       // the previous problem of this warp is done with the workspace
+  if (lane_id() == 0) {
+    *reinterpret_cast<Params*>(solver.ws.prm_mem()) = prm;
+    *reinterpret_cast<ProblemView*>(solver.ws.pb_mem()) = pv;
+  }
+  syncwarp();
   solver.solve(so);
 }
 
