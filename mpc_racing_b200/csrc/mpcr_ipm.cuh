@@ -742,8 +742,6 @@ struct WarpSolver {
   //   rhs 1, 2: the wrap vectors a_1 = e(thr_0) - e(thr_{N-1}), a_2 (steer)
   // Returns false when a pivot block is not positive definite (wrong inertia).
   // -------------------------------------------------------------------------
-  double mz[kRhs][7];   // (dx_{k+1} (6), ds_{k+1}) for the 3 right-hand sides
-  double mw[kRhs][2];   // (dthr_k, dst_k)
 
   MPCR_D bool riccati(double dw) {
     const double Ts = cfg.Ts;
@@ -892,21 +890,7 @@ struct WarpSolver {
       }
     }
     syncwarp();
-    for (int j = 0; j < kRhs; ++j) {
-      for (int a = 0; a < 7; ++a) mz[j][a] = 0.0;
-      mw[j][0] = mw[j][1] = 0.0;
-    }
-    if (act) {
-      const double* src = ws.st(lane) + kOffK;
-      for (int j = 0; j < kRhs; ++j) {
-        if (j < nrhs) {
-          for (int a = 0; a < 7; ++a) mz[j][a] = src[j * 9 + a];
-          mw[j][0] = src[j * 9 + 7];
-          mw[j][1] = src[j * 9 + 8];
-        }
-      }
-    }
-    return true;
+    return true;      // stage k's gain slot now holds (dz_{k+1} (7), dw_k (2)) of the 3 right-hand sides
   }
 
   // -------------------------------------------------------------------------
@@ -918,6 +902,22 @@ struct WarpSolver {
 
   MPCR_D bool kkt_solve(double dw) {
     if (!riccati(dw)) return false;
+    // roll-out results of this lane's stage, read where they are used (they were solver members
+    // once, i.e. a round trip through local memory)
+    double mz[kRhs][7];   // (dx_{k+1} (6), ds_{k+1}) for the 3 right-hand sides
+    double mw[kRhs][2];   // (dthr_k, dst_k)
+    {
+      const int nrhs = cfg.wrap ? kRhs : 1;
+      const double* src = ws.st(act ? lane : 0) + kOffK;
+#pragma unroll
+      for (int j = 0; j < kRhs; ++j) {
+        const bool use = act && j < nrhs;
+#pragma unroll
+        for (int a = 0; a < 7; ++a) mz[j][a] = use ? src[j * 9 + a] : 0.0;
+        mw[j][0] = use ? src[j * 9 + 7] : 0.0;
+        mw[j][1] = use ? src[j * 9 + 8] : 0.0;
+      }
+    }
     // Woodbury: x = x0 + sum_k D_k t_k X_k with (I - M D) t = t0, M_ik = a_i' X_k
     double c1 = 0.0, c2 = 0.0;
     if (cfg.wrap) {
