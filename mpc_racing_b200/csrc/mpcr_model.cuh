@@ -62,6 +62,11 @@ constexpr double Gf = T_max * R / r_wheel;           // wheel force per unit thr
 constexpr double kd = 0.5 * rho * C_d * A_f;
 constexpr double Froll = C_roll * m * g;
 constexpr double cdel = max_steer * 2 * 3.14 / 360.0;  // control/util.py:10-11
+// DERIVATIVE code multiplies by these instead of dividing by the constant (a fp64 division is ~20
+// instructions; 23 of them sat in the once-per-iteration code of the dynamic model).  The VALUE
+// of the model keeps the reference's divisions.
+constexpr double inv_m = 1.0 / m;
+constexpr double inv_Iz = 1.0 / Iz;
 constexpr double g1 = 3.6 * gain1;
 }  // namespace vp
 
@@ -250,9 +255,9 @@ MPCR_HD void lin_dynamic(const double* x, const double* u, double Ts, const doub
     double gA = gFyf[k] * sd + Fyf * cd * gd[k];
     double gB = gFyf[k] * cd - Fyf * sd * gd[k];
     double gfx = (k == 0) ? c.gfx_vx : ((k == 3) ? c.gfx_th : 0.0);
-    gvx[k] = (gfx - gA) / vp::m;
-    gvy[k] = (gB + gFyr[k]) / vp::m;
-    gr[k] = (gB * vp::lf - gFyr[k] * vp::lr) / vp::Iz;
+    gvx[k] = (gfx - gA) * vp::inv_m;
+    gvy[k] = (gB + gFyr[k]) * vp::inv_m;
+    gr[k] = (gB * vp::lf - gFyr[k] * vp::lr) * vp::inv_Iz;
   }
   gvx[1] += r;
   gvx[2] += v_y;
@@ -287,9 +292,9 @@ MPCR_HD void lin_dynamic(const double* x, const double* u, double Ts, const doub
   position_rows(x, Ts, lam, L, hm);
   if (!hm) return;
   // lam-weighted Hessian of the (v_x, v_y, r) rows over q
-  double c1 = lam[3] / vp::m;
-  double c2 = lam[4] / vp::m + lam[5] * vp::lf / vp::Iz;
-  double c3 = lam[4] / vp::m - lam[5] * vp::lr / vp::Iz;
+  double c1 = lam[3] * vp::inv_m;
+  double c2 = lam[4] * vp::inv_m + lam[5] * vp::lf * vp::inv_Iz;
+  double c3 = lam[4] * vp::inv_m - lam[5] * vp::lr * vp::inv_Iz;
   double w = -c1 * sd + c2 * cd;
   double wp = -c1 * cd - c2 * sd;
   Sym5 H;
@@ -361,8 +366,8 @@ MPCR_HD void lin_kinematic(const double* x, const double* u, double Ts, const do
     for (int k = 0; k < 3; ++k) L.d[i][k] = 0.0;
   for (int i = 0; i < 3; ++i)
     for (int k = 0; k < 2; ++k) L.bu[i][k] = 0.0;
-  L.d[0][0] = 1.0 + c.gfx_vx / vp::m * Ts;
-  L.bu[0][0] = c.gfx_th / vp::m * Ts;
+  L.d[0][0] = 1.0 + c.gfx_vx * vp::inv_m * Ts;
+  L.bu[0][0] = c.gfx_th * vp::inv_m * Ts;
   L.d[1][2] = vp::lr;
   double k1 = v_x / Lw * sec2;
   L.d[2][0] = k1 * gd[0] + td / Lw;
@@ -375,7 +380,7 @@ MPCR_HD void lin_kinematic(const double* x, const double* u, double Ts, const do
   if (!hm) return;
   Sym5 H;
   sym5_zero(H);
-  double a = lam[3] * Ts / vp::m;
+  double a = lam[3] * Ts * vp::inv_m;
   H.a[0][0] += a * c.hfx_vxvx;
   H.a[0][3] += a * c.hfx_vxth;
   double l5 = lam[5];
