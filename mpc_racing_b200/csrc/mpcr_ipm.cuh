@@ -1201,8 +1201,10 @@ struct WarpSolver {
         u0 = pbv().u_warm[src];
         u1 = pbv().u_warm[N + src];
       }
-      u[0] = act ? u0 : 0.0;
-      u[1] = act ? u1 : 0.0;
+      // lanes >= N compute along with dummy inputs; non-zero ones, because an exactly zero
+      // numerator sends the model's fp64 divisions down their slow path for the whole warp
+      u[0] = act ? u0 : 0.25;
+      u[1] = act ? u1 : 0.125;
       double xr[6];
       for (int k = 0; k < 6; ++k) { xr[k] = pbv().x0[k]; x[k] = pbv().x0[k]; }
 #pragma unroll 1
