@@ -60,10 +60,14 @@ MPCR_NOINLINE double warp_min(double v) {
   for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m));
   return v;
 }
-MPCR_NOINLINE bool warp_all(bool p) {
+MPCR_D bool warp_all(bool p) {
+#if defined(__CUDA_ARCH__)
+  return __all_sync(0xffffffffu, p) != 0;      // one VOTE instead of a called 5-step butterfly
+#else
   int v = p ? 1 : 0;
   for (int m = 16; m > 0; m >>= 1) v &= shfl_xor_i(v, m);
   return v != 0;
+#endif
 }
 MPCR_D bool warp_any(bool p) { return !warp_all(!p); }
 // NaN-propagating max for finiteness checks
