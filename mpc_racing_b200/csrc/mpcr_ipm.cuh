@@ -1170,12 +1170,12 @@ struct WarpSolver {
         if (row_hasL(r)) {
           const double sl = c.s - lo(r);
           if (d < 0.0) a = fmin(a, -tau * sl / d);
-          g += (-mu / sl + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
+          g += (-mu * (1.0 / sl) + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
         if (row_hasU(r)) {
           const double su = hi(r) - c.s;
           if (d > 0.0) a = fmin(a, tau * su / d);
-          g += (mu / su - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
+          g += (mu * (1.0 / su) - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
       }
       R.dsr[r] = d;
@@ -1705,13 +1705,13 @@ struct WarpSolver {
         const double dyd = (sg + dw) * c.dsr + gb - c.yd;
         R.yd[r] = c.yd + astep * dyd;
         if (row_hasL(r)) {
-          const double sl = c.s - lo(r);
-          const double a = mu / sl - c.vL - c.vL / sl * c.dsr;
+          const double isl = 1.0 / (c.s - lo(r));
+          const double a = (mu - c.vL * c.dsr) * isl - c.vL;      // dvL = S^-1 (mu - vL ds) - vL
           if (a < 0.0) az = fmin(az, -tau * c.vL / a);
         }
         if (row_hasU(r)) {
-          const double su = hi(r) - c.s;
-          const double b = mu / su - c.vU + c.vU / su * c.dsr;
+          const double isu = 1.0 / (hi(r) - c.s);
+          const double b = (mu + c.vU * c.dsr) * isu - c.vU;
           if (b < 0.0) az = fmin(az, -tau * c.vU / b);
         }
       }
@@ -1729,6 +1729,7 @@ struct WarpSolver {
       barB = tp.barB;
       cur_finite = tp.finite;
       row_fetch(0, nx);
+      const double iks = 1.0 / o.kappa_sigma;
       double ntrd = on(0) ? tp_rd[0] : 0.0;
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r) {
@@ -1740,16 +1741,16 @@ struct WarpSolver {
         const double sold = c.s;
         const double snew = sold + astep * c.dsr;
         if (row_hasL(r)) {
-          const double slo = sold - lo(r), sl = snew - lo(r);
-          const double dv = mu / slo - c.vL - c.vL / slo * c.dsr;
+          const double islo = 1.0 / (sold - lo(r)), ms = mu / (snew - lo(r));
+          const double dv = (mu - c.vL * c.dsr) * islo - c.vL;
           const double v = c.vL + az * dv;
-          R.vL[r] = fmax(fmin(v, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl));
+          R.vL[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
         }
         if (row_hasU(r)) {
-          const double suo = hi(r) - sold, su = hi(r) - snew;
-          const double dv = mu / suo - c.vU + c.vU / suo * c.dsr;
+          const double isuo = 1.0 / (hi(r) - sold), ms = mu / (hi(r) - snew);
+          const double dv = (mu + c.vU * c.dsr) * isuo - c.vU;
           const double v = c.vU + az * dv;
-          R.vU[r] = fmax(fmin(v, o.kappa_sigma * mu / su), mu / (o.kappa_sigma * su));
+          R.vU[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
         }
         R.s[r] = snew;
         R.rd[r] = ctrd;
