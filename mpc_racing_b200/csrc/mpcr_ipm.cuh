@@ -576,16 +576,23 @@ struct WarpSolver {
 
   // Sigma_r and d(barrier objective)/d(slack r)
   MPCR_D void sigma_gsb(int r, const RowRegs& c, double& sg, double& g) const {
+    double isl, isu;
+    sigma_gsb(r, c, sg, g, isl, isu);
+  }
+  // ... also hands out the reciprocal slacks 1 / (s - lo), 1 / (hi - s) it computed
+  MPCR_D void sigma_gsb(int r, const RowRegs& c, double& sg, double& g, double& isl, double& isu) const {
     sg = 0.0;
     g = 0.0;
+    isl = 0.0;
+    isu = 0.0;
     if (row_hasL(r)) {
-      const double isl = 1.0 / (c.s - lo(r));
+      isl = 1.0 / (c.s - lo(r));
       sg += c.vL * isl;
       g -= mu * isl;
       if (!row_hasU(r)) g += o.kappa_d * mu;
     }
     if (row_hasU(r)) {
-      const double isu = 1.0 / (hi(r) - c.s);
+      isu = 1.0 / (hi(r) - c.s);
       sg += c.vU * isu;
       g += mu * isu;
       if (!row_hasL(r)) g -= o.kappa_d * mu;
@@ -1700,17 +1707,15 @@ struct WarpSolver {
         const RowRegs c = nx;
         row_fetch(r + 1, nx);
         if (!on(r)) continue;
-        double sg, gb;
-        sigma_gsb(r, c, sg, gb);
+        double sg, gb, isl, isu;
+        sigma_gsb(r, c, sg, gb, isl, isu);
         const double dyd = (sg + dw) * c.dsr + gb - c.yd;
         R.yd[r] = c.yd + astep * dyd;
         if (row_hasL(r)) {
-          const double isl = 1.0 / (c.s - lo(r));
           const double a = (mu - c.vL * c.dsr) * isl - c.vL;      // dvL = S^-1 (mu - vL ds) - vL
           if (a < 0.0) az = fmin(az, -tau * c.vL / a);
         }
         if (row_hasU(r)) {
-          const double isu = 1.0 / (hi(r) - c.s);
           const double b = (mu + c.vU * c.dsr) * isu - c.vU;
           if (b < 0.0) az = fmin(az, -tau * c.vU / b);
         }
