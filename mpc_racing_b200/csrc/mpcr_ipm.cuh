@@ -48,6 +48,24 @@ MPCR_D int shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m);
 
 MPCR_NOINLINE double powd(double x, double y) { return pow(x, y); }
 
+// Reciprocal of a Riccati pivot: hardware seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps, about
+// 1 ulp, 5 instructions and no special-case branch (1.0 / x is ~10 instructions with a slow-path
+// call; three of them sit on the serial critical path of every stage).  Pivots that are not
+// positive are rejected before any of these values is used.
+MPCR_D double rcp_pivot(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 MPCR_NOINLINE double warp_sum(double v) {
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
   return v;
@@ -822,14 +840,14 @@ struct WarpSolver {
       const double h00 = G[9 * kGS + 9], h10 = G[10 * kGS + 9], h20 = G[11 * kGS + 9];
       const double h11 = G[10 * kGS + 10], h21 = G[11 * kGS + 10], h22 = G[11 * kGS + 11];
       const double d0 = h00;
-      const double id0 = 1.0 / d0;
+      const double id0 = rcp_pivot(d0);
       const double l10 = h10 * id0, l20 = h20 * id0;
       const double d1 = h11 - l10 * h10;
-      const double id1 = 1.0 / d1;
+      const double id1 = rcp_pivot(d1);
       const double m21 = h21 - l20 * h10;
       const double l21 = m21 * id1;
       const double d2 = h22 - l20 * h20 - l21 * m21;
-      const double id2 = 1.0 / d2;
+      const double id2 = rcp_pivot(d2);
       // identical in every lane (same inputs, same arithmetic) -> uniform branch
       if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) { ok = false; break; }
       if (lane < 9) {
