@@ -48,7 +48,7 @@ MPCR_D int shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m);
 
 MPCR_NOINLINE double powd(double x, double y) { return pow(x, y); }
 
-// Reciprocal of a Riccati pivot: hardware seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps, about
+// Reciprocal of a Riccati pivot / of a slack: hardware seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps, about
 // 1 ulp, 5 instructions and no special-case branch (1.0 / x is ~10 instructions with a slow-path
 // call; three of them sit on the serial critical path of every stage).  Pivots that are not
 // positive are rejected before any of these values is used.
@@ -604,13 +604,13 @@ struct WarpSolver {
     isl = 0.0;
     isu = 0.0;
     if (row_hasL(r)) {
-      isl = 1.0 / (c.s - lo(r));
+      isl = rcp_pivot(c.s - lo(r));        // slacks are strictly inside their bounds
       sg += c.vL * isl;
       g -= mu * isl;
       if (!row_hasU(r)) g += o.kappa_d * mu;
     }
     if (row_hasU(r)) {
-      isu = 1.0 / (hi(r) - c.s);
+      isu = rcp_pivot(hi(r) - c.s);
       sg += c.vU * isu;
       g += mu * isu;
       if (!row_hasL(r)) g -= o.kappa_d * mu;
@@ -1195,12 +1195,12 @@ struct WarpSolver {
         if (row_hasL(r)) {
           const double sl = c.s - lo(r);
           if (d < 0.0) a = fmin(a, -tau * sl / d);
-          g += (-mu * (1.0 / sl) + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
+          g += (-mu * rcp_pivot(sl) + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
         if (row_hasU(r)) {
           const double su = hi(r) - c.s;
           if (d > 0.0) a = fmin(a, tau * su / d);
-          g += (mu * (1.0 / su) - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
+          g += (mu * rcp_pivot(su) - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
       }
       R.dsr[r] = d;
@@ -1764,13 +1764,13 @@ struct WarpSolver {
         const double sold = c.s;
         const double snew = sold + astep * c.dsr;
         if (row_hasL(r)) {
-          const double islo = 1.0 / (sold - lo(r)), ms = mu / (snew - lo(r));
+          const double islo = rcp_pivot(sold - lo(r)), ms = mu / (snew - lo(r));
           const double dv = (mu - c.vL * c.dsr) * islo - c.vL;
           const double v = c.vL + az * dv;
           R.vL[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
         }
         if (row_hasU(r)) {
-          const double isuo = 1.0 / (hi(r) - sold), ms = mu / (hi(r) - snew);
+          const double isuo = rcp_pivot(hi(r) - sold), ms = mu / (hi(r) - snew);
           const double dv = (mu + c.vU * c.dsr) * isuo - c.vU;
           const double v = c.vU + az * dv;
           R.vU[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
