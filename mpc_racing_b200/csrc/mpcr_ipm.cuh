@@ -1194,12 +1194,12 @@ struct WarpSolver {
         }
         if (row_hasL(r)) {
           const double sl = c.s - lo(r);
-          if (d < 0.0) a = fmin(a, -tau * sl / d);
+          if (d < 0.0) a = fmin(a, -tau * sl * rcp_pivot(d));
           g += (-mu * rcp_pivot(sl) + (row_hasU(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
         if (row_hasU(r)) {
           const double su = hi(r) - c.s;
-          if (d > 0.0) a = fmin(a, tau * su / d);
+          if (d > 0.0) a = fmin(a, tau * su * rcp_pivot(d));
           g += (mu * rcp_pivot(su) - (row_hasL(r) ? 0.0 : o.kappa_d * mu)) * d;
         }
       }
@@ -1731,11 +1731,11 @@ struct WarpSolver {
         R.yd[r] = c.yd + astep * dyd;
         if (row_hasL(r)) {
           const double a = (mu - c.vL * c.dsr) * isl - c.vL;      // dvL = S^-1 (mu - vL ds) - vL
-          if (a < 0.0) az = fmin(az, -tau * c.vL / a);
+          if (a < 0.0) az = fmin(az, -tau * c.vL * rcp_pivot(a));
         }
         if (row_hasU(r)) {
           const double b = (mu + c.vU * c.dsr) * isu - c.vU;
-          if (b < 0.0) az = fmin(az, -tau * c.vU / b);
+          if (b < 0.0) az = fmin(az, -tau * c.vU * rcp_pivot(b));
         }
       }
       az = warp_min(az);
@@ -1764,13 +1764,13 @@ struct WarpSolver {
         const double sold = c.s;
         const double snew = sold + astep * c.dsr;
         if (row_hasL(r)) {
-          const double islo = rcp_pivot(sold - lo(r)), ms = mu / (snew - lo(r));
+          const double islo = rcp_pivot(sold - lo(r)), ms = mu * rcp_pivot(snew - lo(r));
           const double dv = (mu - c.vL * c.dsr) * islo - c.vL;
           const double v = c.vL + az * dv;
           R.vL[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
         }
         if (row_hasU(r)) {
-          const double isuo = rcp_pivot(hi(r) - sold), ms = mu / (hi(r) - snew);
+          const double isuo = rcp_pivot(hi(r) - sold), ms = mu * rcp_pivot(hi(r) - snew);
           const double dv = (mu + c.vU * c.dsr) * isuo - c.vU;
           const double v = c.vU + az * dv;
           R.vU[r] = fmax(fmin(v, o.kappa_sigma * ms), ms * iks);
