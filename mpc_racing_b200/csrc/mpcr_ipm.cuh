@@ -1039,12 +1039,12 @@ struct WarpSolver {
   // One pass gives E_mu for EVERY mu: only the complementarity term depends on mu and
   // max_i |p_i - mu| = max(|p_max - mu|, |p_min - mu|) over the products p_i = slack_i * v_i.
   struct Errors {
-    double dual_inf, pr_inf, prod_max, prod_min, s_d, s_c, viol;
+    double dual_inf, pr_inf, prod_max, prod_min, is_d, is_c, viol;      // is_d = 1 / s_d, is_c = 1 / s_c
     MPCR_D double compl_inf(double mu_t) const {
       return fmax(fabs(prod_max - mu_t), fabs(prod_min - mu_t));
     }
     MPCR_D double E(double mu_t) const {
-      return fmax(dual_inf / s_d, fmax(pr_inf, compl_inf(mu_t) / s_c));
+      return fmax(dual_inf * is_d, fmax(pr_inf, compl_inf(mu_t) * is_c));
     }
   };
   int n_eq_ineq, n_bounds;   // uniform counts: rows with multipliers, bound multipliers
@@ -1095,7 +1095,7 @@ struct WarpSolver {
       for (int a = 0; a < 6; ++a) {
         prinf = fmax(prinf, fabs(dcs[a] * cres[a]));
         vio = fmax(vio, fabs(cres[a]));
-        sum_y += fabs(lam[a] / dcs[a]);
+        sum_y += fabs(lam[a] * rcp_pivot(dcs[a]));
       }
     }
     RowRegs nx{};
@@ -1139,8 +1139,12 @@ struct WarpSolver {
     sum_y = warp_sum(sum_y);
     sum_v = warp_sum(sum_v);
     const double smax = o.s_max;
-    e.s_d = fmax(smax, (sum_y + sum_v) / (double)(n_eq_ineq + n_bounds)) / smax;
-    e.s_c = fmax(smax, sum_v / (double)n_bounds) / smax;
+    // s_d = max(s_max, mean multiplier) / s_max (Waechter & Biegler eq. (6)), kept as reciprocals
+    // (exactly 1 while the mean stays below s_max)
+    const double qd = fmax(smax, (sum_y + sum_v) * rcp_pivot((double)(n_eq_ineq + n_bounds)));
+    const double qc = fmax(smax, sum_v * rcp_pivot((double)n_bounds));
+    e.is_d = (qd == smax) ? 1.0 : smax * rcp_pivot(qd);
+    e.is_c = (qc == smax) ? 1.0 : smax * rcp_pivot(qc);
     return e;
   }
 
