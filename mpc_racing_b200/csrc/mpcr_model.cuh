@@ -87,12 +87,24 @@ MPCR_HD int hm_idx(int i, int j) {  // upper triangle, row-major
   return i * 6 - (i * (i - 1)) / 2 + (j - i);
 }
 
+// x / y for a compile-time constant y: q0 = x * RN(1/y), one FMA residual, one FMA correction
+// (Markstein).  With RN(1/y) correctly rounded this IS the correctly rounded quotient - the same
+// value `x / y` gives (checked bit for bit against the division on the solver fixtures) - in 3
+// instructions and without the division's special-case branch.  Used for the model VALUE, which
+// has to keep the reference's arithmetic.
+template <typename T = void>
+MPCR_HD double div_const(double x, double y, double inv_y) {
+  const double q = x * inv_y;
+  const double r = fma(-q, y, x);
+  return fma(r, inv_y, q);
+}
+
 MPCR_HD double Fx_force(double thr, double v_x) {
   // control/MPC.py:273-283, same operation order as the reference
-  double wheel_rpm = (v_x / vp::C_wheel) * 60;
+  double wheel_rpm = div_const(v_x, vp::C_wheel, 1.0 / vp::C_wheel) * 60;
   double rpm = wheel_rpm * vp::R * 4.5;
   double eta = vp::eta1 * rpm + vp::eta0;
-  double wheel_force = thr * eta * vp::T_max * vp::R / vp::r_wheel;
+  double wheel_force = div_const(thr * eta * vp::T_max * vp::R, vp::r_wheel, 1.0 / vp::r_wheel);
   double drag_force = 0.5 * vp::rho * vp::C_d * vp::A_f * (v_x * v_x);
   double rolling = vp::C_roll * vp::m * vp::g;
   return wheel_force - drag_force - rolling;
@@ -102,7 +114,7 @@ MPCR_HD double steer_angle(double st, double v_x, double v_y) {
   // control/MPC.py:262-271 + control/util.py:10-11
   double vel = sqrt(v_x * v_x + v_y * v_y) * 3.6;
   double gain = vp::gain1 * vel + vp::gain0;
-  return ((st * gain * vp::max_steer) / 360) * 2 * 3.14;
+  return div_const(st * gain * vp::max_steer, 360.0, 1.0 / 360.0) * 2 * 3.14;
 }
 
 MPCR_HD void f_dynamic(const double* x, const double* u, double Ts, double* f) {
@@ -116,9 +128,9 @@ MPCR_HD void f_dynamic(const double* x, const double* u, double Ts, double* f) {
   double Fyr = vp::Cr * (-thr);
   double sd, cd;
   sincos_d(delta, &sd, &cd);
-  double vxd = ((fx - Fyf * sd) / vp::m) + (v_y * r);
-  double vyd = ((Fyf * cd + Fyr) / vp::m) - (v_x * r);
-  double rd = ((Fyf * cd * vp::lf) - (Fyr * vp::lr)) / vp::Iz;
+  double vxd = div_const(fx - Fyf * sd, vp::m, vp::inv_m) + (v_y * r);
+  double vyd = div_const(Fyf * cd + Fyr, vp::m, vp::inv_m) - (v_x * r);
+  double rd = div_const((Fyf * cd * vp::lf) - (Fyr * vp::lr), vp::Iz, vp::inv_Iz);
   double sy, cy;
   sincos_d(yaw, &sy, &cy);
   f[0] = x[0] + (v_x * cy - v_y * sy) * Ts;
@@ -264,9 +276,9 @@ MPCR_HD void lin_dynamic(const double* x, const double* u, double Ts, const doub
   gvy[0] -= r;
   gvy[2] -= v_x;
   if (f) {
-    double vxd = ((c.fx - Fyf * sd) / vp::m) + (v_y * r);
-    double vyd = ((Fyf * cd + Fyr) / vp::m) - (v_x * r);
-    double rd = ((Fyf * cd * vp::lf) - (Fyr * vp::lr)) / vp::Iz;
+    double vxd = div_const(c.fx - Fyf * sd, vp::m, vp::inv_m) + (v_y * r);
+    double vyd = div_const(Fyf * cd + Fyr, vp::m, vp::inv_m) - (v_x * r);
+    double rd = div_const((Fyf * cd * vp::lf) - (Fyr * vp::lr), vp::Iz, vp::inv_Iz);
     double sy, cy;
     sincos_d(x[2], &sy, &cy);
     f[0] = x[0] + (v_x * cy - v_y * sy) * Ts;
