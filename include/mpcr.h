@@ -147,8 +147,9 @@ int mpcr_solve_batch_trace(mpcr_handle* h, int B, const double* x0, const double
                            double* lam_g, double* obj, int32_t* status, int32_t* iters,
                            double* trace, void* cuda_stream);
 
-/* Device time of the last solve kernel launch in milliseconds (CUDA events on
- * the launch stream); blocks until that launch has finished. */
+/* Device time of the last solve in milliseconds: the solve kernel and, when the batch was
+ * reordered (mpcr_config.schedule), the two schedule kernels before it (CUDA events on the
+ * launch stream); blocks until that launch has finished. */
 int mpcr_last_kernel_ms(mpcr_handle* h, float* ms);
 /* Launch geometry of the last solve launch (or of the warp kernel before any launch):
  * blocks, warps per block, dynamic shared bytes. */
