@@ -772,6 +772,8 @@ struct WarpSolver {
   // Returns false when a pivot block is not positive definite (wrong inertia).
   // -------------------------------------------------------------------------
 
+  int ric_nneg;   // negative pivots of the last sweep (uniform)
+
   MPCR_D bool riccati(double dw) {
     const double Ts = cfg.Ts;
     double* T = ws.T();   // [9][kTS]:  columns 0-11 = P M,           12-14 = t_j = p_j + P b_j
@@ -800,6 +802,7 @@ struct WarpSolver {
     }
     syncwarp();
     bool ok = true;
+    ric_nneg = 0;
     const double dwc = dwflag * dw;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
@@ -848,8 +851,20 @@ struct WarpSolver {
       const double l21 = m21 * id1;
       const double d2 = h22 - l20 * h20 - l21 * m21;
       const double id2 = rcp_pivot(d2);
-      // identical in every lane (same inputs, same arithmetic) -> uniform branch
-      if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) { ok = false; break; }
+      // Inertia.  The sweep factorises K0 = the KKT matrix WITHOUT the two wrap rows' terms
+      // Dw a a' (they are added by the Woodbury step of kkt_solve).  IPOPT tests the inertia of
+      // the FULL matrix, and K0 may have up to two negative reduced-Hessian eigenvalues that the
+      // rank-2 positive semidefinite wrap term lifts (the wrap rows carry most of the curvature of
+      // the last throttle, DESIGN.md "Degenerate component").  So negative pivots do not abort the
+      // sweep: they are counted (Sylvester: signs of the pivots = inertia of the reduced Hessian
+      // of K0) and kkt_solve decides with the 2x2 capacitance matrix.  Zero / non-finite pivots and
+      // more negative pivots than the wrap term can lift are wrong inertia right away.
+      // Identical in every lane (same inputs, same arithmetic) -> uniform branch.
+      ric_nneg += (d0 < 0.0 ? 1 : 0) + (d1 < 0.0 ? 1 : 0) + (d2 < 0.0 ? 1 : 0);
+      if (!(fabs(d0) > 0.0 && fabs(d1) > 0.0 && fabs(d2) > 0.0) || ric_nneg > (cfg.wrap ? 2 : 0)) {
+        ok = false;
+        break;
+      }
       if (lane < 9) {
         const int c = lane;
         // rows 9-11 of column c (= entries c of rows 9-11: G is symmetric up to round-off)
@@ -959,6 +974,12 @@ struct WarpSolver {
       const double a00 = 1.0 - Mm[0][0] * Dw[0], a01 = -Mm[0][1] * Dw[1];
       const double a10 = -Mm[1][0] * Dw[0], a11 = 1.0 - Mm[1][1] * Dw[1];
       const double det = a00 * a11 - a01 * a10;
+      // Inertia of the full matrix: with S = -Dw^-1 - A' K0^-1 A = -C Dw^-1 (C = I - M Dw, the matrix
+      // solved here) In(K) = In(K0) + In(S) - In(-Dw^-1), so the reduced Hessian of K is positive
+      // definite iff S has exactly ric_nneg positive eigenvalues: sign(det S) = sign(det C),
+      // trace S = -(C00 / Dw0 + C11 / Dw1).
+      if (ric_nneg == 1 && !(det < 0.0)) return false;
+      if (ric_nneg == 2 && !(det > 0.0 && a00 * Dw[1] + a11 * Dw[0] < 0.0)) return false;
       const double t1 = (a11 * t0[0] - a01 * t0[1]) / det;
       const double t2 = (-a10 * t0[0] + a00 * t0[1]) / det;
       c1 = Dw[0] * t1;
