@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MPCR_VERSION 103
+#define MPCR_VERSION 104
 
 /* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
  * models/BlendedBicycleModel.py:23-46 blend of the two) */
@@ -41,11 +41,13 @@ extern "C" {
 #define MPCR_MODEL_KINEMATIC 1
 #define MPCR_MODEL_BLENDED 2
 
-/* solve kernels: one problem per warp (low latency, small batches) or one problem per
- * lane (throughput, large batches); AUTO picks by batch size */
+/* solve-kernel layouts: one problem per warp (lane k = stage k, any horizon up to 32) or two
+ * problems per warp (one per half-warp, horizons up to 16: the production horizon 15 leaves 17 of
+ * 32 lanes idle otherwise).  AUTO = HALFWARP when N <= 16 and the batch has more than one problem,
+ * else WARP.  Results do not depend on the layout. */
 #define MPCR_KERNEL_AUTO 0
 #define MPCR_KERNEL_WARP 1
-#define MPCR_KERNEL_LANES 2
+#define MPCR_KERNEL_HALFWARP 2
 
 /* integrators of the NLP's dynamics rows (also used by mpcr_model_eval) */
 #define MPCR_INTEGRATOR_EULER 0
@@ -72,7 +74,7 @@ extern "C" {
 
 typedef struct mpcr_config {
   /* problem shape */
-  int32_t N;                 /* horizon, 1..32 (FixedControllerParameters.N = 30) */
+  int32_t N;                 /* horizon, 2..32 (FixedControllerParameters.N = 30): one lane per stage */
   int32_t model;             /* MPCR_MODEL_* */
   int32_t wrap_constraint;   /* keep the i=0 wrap rows of control/MPC.py:142-143 (1 = parity) */
   int32_t lane_constraint;   /* enable the lane row commented out at control/MPC.py:135 */
@@ -94,8 +96,8 @@ typedef struct mpcr_config {
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
   double mu_init;
   int32_t solve_kernel;      /* MPCR_KERNEL_* (0 = auto) */
-  int32_t integrator;        /* MPCR_INTEGRATOR_EULER (reference, default) or MPCR_INTEGRATOR_RK4 (extension;
-                              * solved by the lane kernel) */
+  int32_t integrator;        /* MPCR_INTEGRATOR_EULER (reference, default) or MPCR_INTEGRATOR_RK4 (extension:
+                              * the dynamics rows become x_i = RK4(x_{i-1}, u_{i-1}), same kernel) */
   int32_t restoration;       /* 1: when the filter line search fails, run the feasibility-restoration phase
                               * (IPOPT would; quadratic-penalty variant) instead of returning
                               * MPCR_RESTORATION_FAILED.  Selects the kernel build that contains the phase
@@ -104,6 +106,11 @@ typedef struct mpcr_config {
                               * Results do not depend on it; kernel time does (stragglers picked last leave
                               * the GPU idle).  0 = auto: expected-longest-first (reference-path curvature)
                               * for batches larger than one wave of resident warps */
+  double polish_tol;         /* > 0 (and < tol): after a problem terminates successfully the iteration continues
+                              * until the optimality error is below polish_tol (or the line search gives up);
+                              * status[] / iters[] still report the first termination, U/X/S/obj/lam_g the
+                              * polished point.  Test / analysis aid: two solvers that stop at tol = 1e-4 agree
+                              * only to ~1e-3 in flat directions, polished points agree to ~1e-8.  0 = off */
 } mpcr_config;
 
 typedef struct mpcr_handle mpcr_handle;

@@ -32,6 +32,7 @@ class MpcrConfig(C.Structure):
         ("compl_inf_tol", C.c_double), ("mu_init", C.c_double),
         ("solve_kernel", C.c_int32), ("integrator", C.c_int32),
         ("restoration", C.c_int32), ("schedule", C.c_int32),
+        ("polish_tol", C.c_double),
     ]
 
 

@@ -1,11 +1,12 @@
 // libmpcr.so: CUDA kernels + the C ABI of include/mpcr.h.
 //
-// Build (see __graft_entry__.build):
+// Build (see mpc_racing_b200/build.py):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 //
-// Solve kernel: persistent, one warp (= one block of 32 threads) per problem,
-// problems handed out through an atomic counter so that converged problems free
-// their warp immediately.  No tensor cores (9x9 / 3x3 fp64 blocks), no CPU path.
+// Solve kernel (mpcr_solve_variant.cu, one translation unit per template variant): persistent,
+// one warp (= one block of 32 threads) per problem - or per two problems when the horizon fits a
+// half-warp; problems handed out through an atomic counter so that converged problems free
+// their lanes immediately.  No tensor cores (9x9 / 3x3 fp64 blocks), no CPU path.
 #include <cuda_runtime.h>
 
 #include <stdlib.h>
@@ -17,78 +18,27 @@
 #include <vector>
 
 #include "mpcr_config.h"
-#include "mpcr_ipm.cuh"
-#include "mpcr_ipm_lanes.cuh"
+#include "mpcr_solve_kernel.cuh"
 #include "mpcr_track.cuh"
 
 namespace mpcr {
 
-// STAGE_GLOBAL: the per-stage Riccati storage lives in a per-block global slab (L1/L2
-// resident) instead of shared memory; shared memory then only holds the ~4 KB scratch.
-#ifndef MPCR_MIN_BLOCKS
-#define MPCR_MIN_BLOCKS 1
-#endif
-template <int MODEL, bool STAGE_GLOBAL, bool RESTO>
-__global__ void __launch_bounds__(32, MPCR_MIN_BLOCKS)
-solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
-             int trace_rows, int* __restrict__ counter, double* __restrict__ slabs,
-             const int* __restrict__ order) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31;
-  double* stage = STAGE_GLOBAL ? slabs + (size_t)blockIdx.x * stage_doubles(cfg.N) : nullptr;
-  while (true) {
-    int b = 0;
-    if (lane == 0) {
-      b = atomicAdd(counter, 1);
-      if (order && b < B) b = order[b];      // dispatch order (schedule kernels below); results do not depend on it
-    }
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= B) break;
-    solve_problem<MODEL, STAGE_GLOBAL, RESTO>(cfg, in, out, b, trace_rows, smem, stage);
-    __syncwarp();
+template <> SolveKernelFn solve_kernel_table<false, 0, false>(int);
+template <> SolveKernelFn solve_kernel_table<false, 0, true>(int);
+template <> SolveKernelFn solve_kernel_table<false, 1, false>(int);
+template <> SolveKernelFn solve_kernel_table<false, 1, true>(int);
+template <> SolveKernelFn solve_kernel_table<true, 0, false>(int);
+template <> SolveKernelFn solve_kernel_table<true, 0, true>(int);
+template <> SolveKernelFn solve_kernel_table<true, 1, false>(int);
+template <> SolveKernelFn solve_kernel_table<true, 1, true>(int);
+
+SolveKernelFn solve_kernel_variant(int model, bool resto, int ig, bool half) {
+  if (resto) {
+    if (ig) return half ? solve_kernel_table<true, 1, true>(model) : solve_kernel_table<true, 1, false>(model);
+    return half ? solve_kernel_table<true, 0, true>(model) : solve_kernel_table<true, 0, false>(model);
   }
-}
-
-typedef void (*SolveKernelFn)(const Config, const BatchIn, const BatchOut, int, int, int*, double*, const int*);
-
-template <bool SG, bool RS>
-static SolveKernelFn pick_kernel_m(int model) {
-  if (model == kDynamic) return solve_kernel<kDynamic, SG, RS>;
-  if (model == kKinematic) return solve_kernel<kKinematic, SG, RS>;
-  return solve_kernel<kBlended, SG, RS>;
-}
-
-// restoration: the kernel build that contains the feasibility-restoration phase (the plain build
-// carries none of its code or registers)
-static SolveKernelFn pick_kernel(int model, bool stage_global, bool restoration) {
-  if (stage_global) return restoration ? pick_kernel_m<true, true>(model) : pick_kernel_m<true, false>(model);
-  return restoration ? pick_kernel_m<false, true>(model) : pick_kernel_m<false, false>(model);
-}
-
-// Throughput kernel: one problem per LANE (mpcr_ipm_lanes.cuh).  Block = one warp; warp w owns
-// the workspace slab [w * ws_doubles * 32, ...) laid out [element][lane] (coalesced).
-template <int MODEL, int IG>
-__global__ void __launch_bounds__(32, 1)
-lane_solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
-                  int trace_rows, double* __restrict__ ws, int ws_doubles) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 32 + lane;
-  if (b >= B) return;
-  double* w = ws + (size_t)blockIdx.x * ws_doubles * 32 + lane;
-  lane_solve_problem<MODEL, IG>(cfg, in, out, b, trace_rows, w);
-}
-
-typedef void (*LaneKernelFn)(const Config, const BatchIn, const BatchOut, int, int, double*, int);
-
-static LaneKernelFn pick_lane_kernel(int model, int integrator) {
-  if (integrator == MPCR_INTEGRATOR_RK4) {
-    if (model == kDynamic) return lane_solve_kernel<kDynamic, 1>;
-    if (model == kKinematic) return lane_solve_kernel<kKinematic, 1>;
-    return lane_solve_kernel<kBlended, 1>;
-  }
-  if (model == kDynamic) return lane_solve_kernel<kDynamic, 0>;
-  if (model == kKinematic) return lane_solve_kernel<kKinematic, 0>;
-  return lane_solve_kernel<kBlended, 0>;
+  if (ig) return half ? solve_kernel_table<false, 1, true>(model) : solve_kernel_table<false, 1, false>(model);
+  return half ? solve_kernel_table<false, 0, true>(model) : solve_kernel_table<false, 0, false>(model);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -181,21 +131,18 @@ struct mpcr_handle {
   std::string err;
   int device = 0;
   int num_sms = 0;
-  int blocks_per_sm = 0;
-  int smem_bytes = 0;
   int* d_counter = nullptr;
-  double* d_slabs = nullptr;
-  bool stage_global = false;
-  SolveKernelFn kernel = nullptr;
-  LaneKernelFn lane_kernel = nullptr;
+  // layout: one problem per warp (any N <= 32) or two per warp (N <= 16); AUTO picks the half-warp
+  // layout when it fits and the batch has more problems than the GPU holds warps (a problem that
+  // can have a warp of its own is solved faster there)
+  struct Layout {
+    SolveKernelFn kernel = nullptr;
+    int smem_bytes = 0;
+    int blocks_per_sm = 0;
+  } warp, half;
   int kernel_sel = MPCR_KERNEL_AUTO;     // config / MPCR_KERNEL env
-  // AUTO: batches at least this large use the lane kernel.  Measured on B200 (profiles/r1e_*):
-  // at B = 16384 the lane kernel is 4x SLOWER than the warp kernel (16k threads cannot hide the
-  // HBM latency of its global-memory workspace), so AUTO never selects it unless the
-  // MPCR_LANES_MIN_BATCH environment variable lowers this threshold.
-  int lanes_min_batch = 1 << 30;
-  double* d_lane_ws = nullptr;           // lane-kernel workspace, grown on demand
-  size_t lane_ws_warps = 0;
+  cudaEvent_t ev_done = nullptr;         // end of the last launch: orders launches from different streams
+  bool launched = false;
   int last_blocks = 0, last_smem = 0;    // geometry of the last launch
   int schedule = MPCR_SCHEDULE_AUTO;     // config / MPCR_SCHEDULE env
   int* d_order = nullptr;                // dispatch order [order_cap] | histogram + cursors [2 * 256]
@@ -245,19 +192,11 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
-  {
-    const char* e = getenv("MPCR_STAGE_GLOBAL");
-    h->stage_global = e ? (atoi(e) != 0) : false;
-  }
-  h->kernel = pick_kernel(h->cfg.model, h->stage_global, h->cfg.o.restoration != 0);
-  h->lane_kernel = pick_lane_kernel(h->cfg.model, h->cfg.integrator);
   h->kernel_sel = cfg->solve_kernel;
   {
     const char* e = getenv("MPCR_KERNEL");
     if (e && !strcmp(e, "warp")) h->kernel_sel = MPCR_KERNEL_WARP;
-    if (e && !strcmp(e, "lanes")) h->kernel_sel = MPCR_KERNEL_LANES;
-    const char* m = getenv("MPCR_LANES_MIN_BATCH");
-    if (m && atoi(m) > 0) h->lanes_min_batch = atoi(m);
+    if (e && !strcmp(e, "half") && h->cfg.N <= 16) h->kernel_sel = MPCR_KERNEL_HALFWARP;
   }
   h->schedule = cfg->schedule;
   {
@@ -265,32 +204,33 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
     if (e && !strcmp(e, "index")) h->schedule = MPCR_SCHEDULE_INDEX;
     if (e && !strcmp(e, "curvature")) h->schedule = MPCR_SCHEDULE_CURVATURE;
   }
-  CK(cudaFuncSetAttribute(h->lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-  h->smem_bytes = (h->stage_global ? kScratch : ws_doubles(h->cfg.N)) * (int)sizeof(double);
-  CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  if (!h->stage_global) {
-    h->carve_env = -1;
+  h->carve_env = -1;
+  {
     const char* e = getenv("MPCR_CARVEOUT");      // percent of the unified L1/shared array
     if (e && atoi(e) > 0 && atoi(e) <= 100) h->carve_env = atoi(e);
+  }
+  const bool resto = h->cfg.o.restoration != 0;
+  const int ig = h->cfg.integrator;
+  for (int half = 0; half < 2; ++half) {
+    if (half && h->cfg.N > 16) break;
+    mpcr_handle::Layout& L = half ? h->half : h->warp;
+    L.kernel = solve_kernel_variant(h->cfg.model, resto, ig, half != 0);
+    L.smem_bytes = (half ? 2 : 1) * ws_doubles(h->cfg.N, ig) * (int)sizeof(double);
+    CK(cudaFuncSetAttribute(L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     h->carve_now = h->carve_env > 0 ? h->carve_env : (int)cudaSharedmemCarveoutMaxShared;
-    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carve_now));
-  }
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, 32,
-                                                   h->smem_bytes));
-  if (h->blocks_per_sm < 1) {
-    h->err = "solve kernel does not fit on this device";
-    return MPCR_ERR_CUDA;
-  }
-  {
+    CK(cudaFuncSetAttribute(L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carve_now));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.blocks_per_sm, L.kernel, 32, L.smem_bytes));
+    if (L.blocks_per_sm < 1) {
+      h->err = "solve kernel does not fit on this device";
+      return MPCR_ERR_CUDA;
+    }
     const char* e = getenv("MPCR_BLOCKS_PER_SM");
-    if (e && atoi(e) > 0 && atoi(e) < h->blocks_per_sm) h->blocks_per_sm = atoi(e);
+    if (e && atoi(e) > 0 && atoi(e) < L.blocks_per_sm) L.blocks_per_sm = atoi(e);
   }
-  if (h->stage_global)
-    CK(cudaMalloc(&h->d_slabs, (size_t)h->num_sms * h->blocks_per_sm * stage_doubles(h->cfg.N) *
-                                   sizeof(double)));
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   return MPCR_OK;
 }
 
@@ -298,14 +238,13 @@ extern "C" int mpcr_destroy(mpcr_handle* h) {
   if (!h) return MPCR_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->d_counter) cudaFree(h->d_counter);
-  if (h->d_slabs) cudaFree(h->d_slabs);
-  if (h->d_lane_ws) cudaFree(h->d_lane_ws);
   if (h->d_order) cudaFree(h->d_order);
   if (h->d_bin) cudaFree(h->d_bin);
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->d_ibuf) cudaFree(h->d_ibuf);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   delete h;
   return MPCR_OK;
 }
@@ -317,9 +256,9 @@ extern "C" int mpcr_lam_g_stride(mpcr_handle* h) {
 
 extern "C" int mpcr_launch_info(mpcr_handle* h, int* blocks, int* warps_per_block, int* smem) {
   if (!h) return MPCR_ERR_INVALID_ARG;
-  if (blocks) *blocks = h->last_blocks ? h->last_blocks : h->num_sms * h->blocks_per_sm;
+  if (blocks) *blocks = h->last_blocks ? h->last_blocks : h->num_sms * h->warp.blocks_per_sm;
   if (warps_per_block) *warps_per_block = 1;
-  if (smem) *smem = h->last_blocks ? h->last_smem : h->smem_bytes;
+  if (smem) *smem = h->last_blocks ? h->last_smem : h->warp.smem_bytes;
   return MPCR_OK;
 }
 
@@ -340,51 +279,36 @@ extern "C" int mpcr_last_kernel_ms(mpcr_handle* h, float* ms) {
 
 static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut& out,
                         int trace_rows, cudaStream_t st) {
-  const bool lanes = h->kernel_sel == MPCR_KERNEL_LANES || h->cfg.integrator == MPCR_INTEGRATOR_RK4 ||
-                     (h->kernel_sel == MPCR_KERNEL_AUTO && B >= h->lanes_min_batch);
-  const size_t warps = ((size_t)B + 31) / 32;
-  const int wsd = lane_ws_doubles(h->cfg.N);
-  if (lanes) {
-    if (warps > h->lane_ws_warps) {
-      if (h->d_lane_ws) cudaFree(h->d_lane_ws);
-      h->d_lane_ws = nullptr;
-      h->lane_ws_warps = 0;
-      CK(cudaMalloc(&h->d_lane_ws, warps * (size_t)wsd * 32 * sizeof(double)));
-      h->lane_ws_warps = warps;
-    }
-  }
-  if (lanes) {
-    CK(cudaEventRecord(h->ev0, st));
-    h->lane_kernel<<<(unsigned)warps, 32, 0, st>>>(h->cfg, in, out, B, trace_rows, h->d_lane_ws, wsd);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, st));
-    h->timed = true;
-    h->last_blocks = (int)warps;
-    h->last_smem = 0;
-    h->last_launches = 1;
-    return MPCR_OK;
-  }
-  int grid = h->num_sms * h->blocks_per_sm;
-  if (grid > B) grid = B;
+  // The handle's dispatch counter, order buffers and timing events are shared by all of its
+  // launches: a launch on another stream than the previous one waits for that one first.
+  if (h->launched) CK(cudaStreamWaitEvent(st, h->ev_done, 0));
+  const bool use_half = h->half.kernel != nullptr &&
+                        (h->kernel_sel == MPCR_KERNEL_HALFWARP ||
+                         (h->kernel_sel == MPCR_KERNEL_AUTO && B > h->num_sms * h->warp.blocks_per_sm));
+  const mpcr_handle::Layout& L = use_half ? h->half : h->warp;
+  const int per_block = use_half ? 2 : 1;
+  int grid = h->num_sms * L.blocks_per_sm;
+  const int need = (B + per_block - 1) / per_block;
+  if (grid > need) grid = need;
   h->last_blocks = grid;
-  h->last_smem = h->smem_bytes;
-  if (!h->stage_global && h->carve_env < 0) {
+  h->last_smem = L.smem_bytes;
+  if (h->carve_env < 0) {
     // Small batches leave shared memory unused: give it to L1, where the per-lane local-memory
     // arrays live (measured: B = 1 3.99 -> 3.32 ms, B = 256 17.4 -> 14.4 ms).  Full grids keep the
-    // maximum shared carve-out (7 resident warps per SM).
+    // maximum shared carve-out.
     const int resident = (grid + h->num_sms - 1) / h->num_sms;
     int carve = (int)cudaSharedmemCarveoutMaxShared;
-    if (resident < h->blocks_per_sm) {
-      carve = (int)((100.0 * resident * (h->smem_bytes + 1024)) / (228.0 * 1024.0)) + 1;
+    if (resident < L.blocks_per_sm) {
+      carve = (int)((100.0 * resident * (L.smem_bytes + 1024)) / (228.0 * 1024.0)) + 1;
       if (carve > 100) carve = 100;
     }
     // set on every launch: the attribute belongs to the kernel function, not to this handle
     // (another handle may have changed it)
-    CK(cudaFuncSetAttribute(h->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    CK(cudaFuncSetAttribute(L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     h->carve_now = carve;
   }
   const bool sched = h->schedule == MPCR_SCHEDULE_CURVATURE ||
-                     (h->schedule == MPCR_SCHEDULE_AUTO && B > grid);
+                     (h->schedule == MPCR_SCHEDULE_AUTO && B > grid * per_block);
   if (sched && B > h->order_cap) {
     if (h->d_order) cudaFree(h->d_order);
     if (h->d_bin) cudaFree(h->d_bin);
@@ -409,9 +333,11 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
     order = h->d_order;
     h->last_launches = 3;
   }
-  h->kernel<<<grid, 32, h->smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, h->d_slabs, order);
+  L.kernel<<<grid, 32, L.smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, order);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, st));
+  CK(cudaEventRecord(h->ev_done, st));
+  h->launched = true;
   h->timed = true;
   return MPCR_OK;
 }

@@ -44,6 +44,7 @@ inline void config_default(mpcr_config* c) {
   c->integrator = MPCR_INTEGRATOR_EULER;
   c->restoration = 0;
   c->schedule = MPCR_SCHEDULE_AUTO;
+  c->polish_tol = 0.0;
 }
 
 inline void config_convert(const mpcr_config& c, Config* out) {
@@ -121,6 +122,7 @@ inline void config_convert(const mpcr_config& c, Config* out) {
   o.resto_max_iter = 100;
   o.resto_weight = 1.0;
   o.kappa_resto = 0.9;
+  o.polish_tol = c.polish_tol;
 }
 
 inline bool config_valid(const mpcr_config& c, const char** why) {
@@ -133,10 +135,12 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.integrator < 0 || c.integrator > 1) { *why = "unknown integrator"; return false; }
   if (c.restoration < 0 || c.restoration > 1) { *why = "restoration must be 0 or 1"; return false; }
   if (c.schedule < 0 || c.schedule > 2) { *why = "unknown schedule"; return false; }
-  if (c.integrator == MPCR_INTEGRATOR_RK4 && c.solve_kernel == MPCR_KERNEL_WARP) {
-    *why = "the RK4 integrator is implemented by the lane kernel only";
+  if (c.solve_kernel == MPCR_KERNEL_HALFWARP && c.N > 16) {
+    *why = "the half-warp layout holds horizons up to 16";
     return false;
   }
+  if (!(c.polish_tol >= 0.0)) { *why = "polish_tol must be >= 0"; return false; }
+  if (!(c.tol > 0.0) || !(c.acceptable_tol > 0.0)) { *why = "tol and acceptable_tol must be positive"; return false; }
   return true;
 }
 

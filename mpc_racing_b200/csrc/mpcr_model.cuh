@@ -13,7 +13,7 @@ namespace mpcr {
 // wrapped in non-inlined functions so that the solve kernel's hot loop stays inside the SM's
 // instruction cache (profiles/r1a: the first version was instruction-fetch bound).
 #if defined(__CUDACC__)
-#define MPCR_MATH __host__ __device__ __noinline__
+#define MPCR_MATH static __host__ __device__ __noinline__
 #else
 #define MPCR_MATH inline
 #endif

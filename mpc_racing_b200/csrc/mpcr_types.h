@@ -50,6 +50,7 @@ struct IpmOptions {
   int restoration;
   int resto_max_iter;
   double resto_weight, kappa_resto;
+  double polish_tol;     // > 0: keep iterating to this tolerance after the first termination
 };
 
 struct Config {
@@ -58,7 +59,7 @@ struct Config {
   int model;        // Model
   int wrap;         // keep the i=0 wrap-around rate rows of control/MPC.py:142-143
   int lane_con;     // enable the lane row commented out at control/MPC.py:135
-  int integrator;   // 0 = explicit Euler (reference), 1 = RK4 (extension; lane kernel only)
+  int integrator;   // 0 = explicit Euler (reference), 1 = RK4 (extension)
   Params p;
   IpmOptions o;
 };

@@ -51,7 +51,7 @@ class BatchedMPC:
                  runtime_params: Optional[RuntimeControllerParameters] = None,
                  wrap_constraint=True, lane_constraint=False, device=0, on_device=False,
                  tol=1e-4, acceptable_tol=1e-2, max_iter=None, honor_instance_d_max=False,
-                 solve_kernel=0, integrator="euler", restoration=False, schedule="auto"):
+                 solve_kernel=0, integrator="euler", restoration=False, schedule="auto", polish_tol=0.0):
         self.lib = _capi.load_library()
         fp = fixed_params or FixedControllerParameters()
         rp = runtime_params or RuntimeControllerParameters()
@@ -76,13 +76,15 @@ class BatchedMPC:
         cfg.d_max = float(rp.d_max if honor_instance_d_max else RuntimeControllerParameters.d_max)
         cfg.tol = float(tol)
         cfg.acceptable_tol = float(acceptable_tol)
-        # 0 = auto (by batch size), 1 = one problem per warp, 2 = one problem per lane
-        cfg.solve_kernel = int({"auto": 0, "warp": 1, "lanes": 2}.get(solve_kernel, solve_kernel))
-        # "euler" = the reference's discretisation; "rk4" = extension, solved by the lane kernel
+        # layout: 0 = auto, 1 = one problem per warp, 2 = two problems per warp (horizons up to 16)
+        cfg.solve_kernel = int({"auto": 0, "warp": 1, "half": 2}.get(solve_kernel, solve_kernel))
+        # "euler" = the reference's discretisation; "rk4" = extension (same kernel, 32-entry stage Jacobian)
         cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
         cfg.restoration = int(bool(restoration))     # feasibility restoration phase; off = status -2 instead
         # dispatch order of the batch: "auto" = expected-longest-first for batches above one wave
         cfg.schedule = int({"auto": 0, "index": 1, "curvature": 2}.get(schedule, schedule))
+        # > 0: keep iterating to this tolerance after the first termination (status / iters report the first)
+        cfg.polish_tol = float(polish_tol)
         self.cfg = cfg
         self.N = cfg.N
         self.on_device = bool(on_device)

@@ -33,7 +33,6 @@ def emu_lib():
         _lib.emu_config_default.argtypes = [C.POINTER(MpcrConfig)]
         _lib.emu_lam_g_stride.argtypes = [C.POINTER(MpcrConfig)]
         _lib.emu_solve_batch.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
-        _lib.emu_solve_batch_lanes.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
     return _lib
 
 
@@ -41,11 +40,14 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def emu_solve(x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None, trace=False, lanes=False,
+def emu_solve(x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None, trace=False, half=False,
               **cfg_kw):
+    """half=True: the two-problems-per-warp layout (horizons up to 16)."""
     lib = emu_lib()
     cfg = MpcrConfig()
     lib.emu_config_default(C.byref(cfg))
+    if half:
+        cfg.solve_kernel = 2
     for k, v in cfg_kw.items():
         assert hasattr(cfg, k), k
         setattr(cfg, k, v)
@@ -57,7 +59,7 @@ def emu_solve(x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None, tr
                eC=np.zeros((B, N)), eL=np.zeros((B, N)), lam_g=np.zeros((B, ls)), obj=np.zeros(B),
                status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
     tr = np.zeros((B, cfg.max_iter + 1, 8)) if trace else None
-    fn = lib.emu_solve_batch_lanes if lanes else lib.emu_solve_batch
+    fn = lib.emu_solve_batch
     rc = fn(C.byref(cfg), B, _ptr(x0), _ptr(u_prev), _ptr(s0), _ptr(cx), _ptr(cy),
                              _ptr(max_err), _ptr(params), _ptr(u_warm), _ptr(out['U']), _ptr(out['X']),
                              _ptr(out['S']), _ptr(out['eC']), _ptr(out['eL']), _ptr(out['lam_g']),

@@ -35,10 +35,9 @@ def test_oracle_returns_the_acceptable_point():
         assert r["iters"] == ORACLE_ITERS[b]
 
 
-@pytest.mark.parametrize("lanes", [False, True])
-def test_solver_sources_return_the_acceptable_point(lanes):
+def test_solver_source_returns_the_acceptable_point():
     d = _fixture()
-    r = emu_solve(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"], params=d["params"], lanes=lanes, **KW)
+    r = emu_solve(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"], params=d["params"], **KW)
     assert list(r["status"]) == [1, 1, 1, 1]
     # round-off decides where exactly the stalled line search gives up
     assert np.abs(r["iters"] - np.array(ORACLE_ITERS)).max() <= 16
@@ -48,7 +47,7 @@ def test_solver_sources_return_the_acceptable_point(lanes):
 def test_acceptable_exit_on_gpu():
     from mpc_racing_b200.solver import BatchedMPC
     d = _fixture()
-    for kern in ("warp", "lanes"):
+    for kern in ("warp",):
         s = BatchedMPC(N=32, Ts=0.04, model="kinematic", solve_kernel=kern)
         r = s.solve(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"], params=d["params"])
         assert list(r.status) == [1, 1, 1, 1], (kern, r.status)

@@ -16,23 +16,21 @@ def cfg2():
 
 
 # ---- CPU: the kernel sources compiled for the host (tests/emu) and the config checks ----------
-@pytest.mark.parametrize("N", [2, 32])
-@pytest.mark.parametrize("lanes", [False, True])
-def test_horizon_limits(cfg2, N, lanes):
-    """N = 2 (smallest) and N = 32 (one warp lane per stage: the largest) against the oracle."""
+@pytest.mark.parametrize("N,half", [(2, False), (2, True), (16, True), (32, False)])
+def test_horizon_limits(cfg2, N, half):
+    """N = 2 (smallest), N = 16 (the largest the half-warp layout holds) and N = 32 (one warp lane per
+    stage: the largest) against the oracle."""
     from emu_util import emu_solve
     i = [7]
-    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], N=N, lanes=lanes)
+    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], N=N, half=half)
     ref = oracle_solve(cfg2['x0'][7], cfg2['u_prev'][7], cfg2['s0'][7], cfg2['cx'][7], cfg2['cy'][7], N=N)
     assert_parity(out, 0, ref)
 
 
-@pytest.mark.parametrize("lanes", [False, True])
-def test_iteration_cap_reports_maxiter(cfg2, lanes):
+def test_iteration_cap_reports_maxiter(cfg2):
     from emu_util import emu_solve
     i = [0, 1]
-    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], max_iter=5,
-                    lanes=lanes)
+    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], max_iter=5)
     assert (out['status'] == -1).all() and (out['iters'] == 5).all()      # Maximum_Iterations_Exceeded
     assert np.isfinite(out['U']).all() and np.isfinite(out['X']).all()
     ref = oracle_solve(cfg2['x0'][0], cfg2['u_prev'][0], cfg2['s0'][0], cfg2['cx'][0], cfg2['cy'][0],
@@ -42,7 +40,7 @@ def test_iteration_cap_reports_maxiter(cfg2, lanes):
 
 
 @pytest.mark.parametrize("field,value", [("N", 33), ("N", 1), ("Ts", 0.0), ("model", 3), ("max_iter", -1),
-                                         ("solve_kernel", 7), ("integrator", 2)])
+                                         ("solve_kernel", 7), ("integrator", 2), ("polish_tol", -1.0), ("tol", 0.0)])
 def test_invalid_config_is_rejected(field, value):
     lib = _capi.load_library()
     cfg = _capi.default_config(lib)
@@ -52,8 +50,8 @@ def test_invalid_config_is_rejected(field, value):
     assert not h
 
 
-@pytest.mark.parametrize("lanes", [False, True])
-def test_pathological_inputs_terminate_with_failure_codes(cfg2, lanes):
+@pytest.mark.parametrize("N,half", [(30, False), (15, True)])
+def test_pathological_inputs_terminate_with_failure_codes(cfg2, N, half):
     """NaN / Inf / singular inputs never hang or poison neighbours: each problem ends with a failure
     status (control/MPC.py:172-181 convention: last iterate, sol = None)."""
     from emu_util import emu_solve
@@ -65,7 +63,7 @@ def test_pathological_inputs_terminate_with_failure_codes(cfg2, lanes):
     x0[4, 3] = 0.0
     x0[4, 4] = 0.0                     # |v| = 0: the steering-gain derivative divides by it
     s0[5] = 1e9                        # absurd progress
-    r = emu_solve(x0, cfg2['u_prev'][idx], s0, cx, cfg2['cy'][idx], lanes=lanes, max_iter=60)
+    r = emu_solve(x0, cfg2['u_prev'][idx], s0, cx, cfg2['cy'][idx], N=N, half=half, max_iter=60)
     assert list(r['status'][:3]) == [-4, -4, -4]            # Invalid_Number_Detected
     assert r['status'][3] == 0                               # the untouched neighbour converges
     assert r['status'][4] < 0 and r['status'][5] < 0

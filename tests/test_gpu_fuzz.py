@@ -1,8 +1,9 @@
-"""GPU fuzz: the two independent CUDA mappings of the same algorithm (warp-per-problem and
-lane-per-problem kernels) against each other over random configurations - horizon, step, model, lane
-row, wrap rows, restoration, NaN previous inputs, per-problem controller parameters (well outside the
-reference's ranges: badly scaled objectives), warm starts.  Statuses must agree, and where the
-iteration counts agree the objectives agree to round-off."""
+"""GPU fuzz: the CUDA solver against the independent compiled CPU oracle (oracle/cxx: AD derivatives,
+block-tridiagonal LDL^T) and, for horizons up to 16, its two lane layouts against each other, over
+random configurations - horizon, step, model, lane row, wrap rows, restoration, NaN previous inputs,
+per-problem controller parameters (well outside the reference's ranges: badly scaled objectives),
+warm starts.  Success / failure must agree problem by problem; where the iteration counts agree the
+objectives agree to round-off; the two layouts are bit-identical."""
 import numpy as np
 import pytest
 
@@ -52,14 +53,30 @@ def compare(a, b):
                 finite=bool(np.isfinite(a.U).all() and np.isfinite(b.U).all()))
 
 
-def test_warp_and_lane_kernels_agree_on_random_configurations():
+class _R:
+    def __init__(self, d):
+        self.__dict__.update(d)
+
+
+def oracle_cxx(kw, args, opt):
+    from oracle import cxx
+    o = cxx.solve_batch(*args, N=kw["N"], Ts=kw["Ts"], model=kw["model"], wrap=kw["wrap_constraint"],
+                        lane=kw["lane_constraint"], restoration=kw["restoration"], **opt)
+    return _R(o)
+
+
+def test_kernel_agrees_with_the_compiled_oracle_on_random_configurations():
     from mpc_racing_b200.solver import BatchedMPC
     for trial, name, B, kw, args, opt in fuzz_trials(30):
         a = BatchedMPC(solve_kernel="warp", **kw).solve(*args, **opt)
-        b = BatchedMPC(solve_kernel="lanes", **kw).solve(*args, **opt)
+        b = oracle_cxx(kw, args, opt)
         m = compare(a, b)
         ctx = f"trial {trial} {name} B={B} {kw}: {m}"
         assert m["finite"], ctx
         assert m["class_eq"] >= 0.97, ctx            # success / failure, problem by problem
         assert m["worst_same"] <= 1e-7, ctx          # same iteration count => same result
         assert m["obj_close"] >= 0.95, ctx
+        if kw["N"] <= 16:
+            h = BatchedMPC(solve_kernel="half", **kw).solve(*args, **opt)
+            for k in ("U", "X", "S", "lam_g", "obj", "status", "iters"):
+                assert np.array_equal(getattr(a, k), getattr(h, k), equal_nan=True), (ctx, k)

@@ -29,7 +29,7 @@ def test_oracle_ipm_reaches_the_independent_optimum():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", ["warp", "lanes"])
+@pytest.mark.parametrize("kernel", ["warp"])
 def test_cuda_kernels_reach_the_independent_optimum(kernel):
     from mpc_racing_b200.solver import BatchedMPC
     d = load_fixture("cfg2_shanghai_4096.npz")

@@ -1,7 +1,7 @@
-"""Memory-safety of the solver sources: both solvers (warp-per-problem through the SIMT emulator,
-lane-per-problem natively) are compiled for the host with AddressSanitizer + UBSan and run over the
-shape variants (horizons 2/15/32, models, lane rows, no wrap rows, warm start, RK4).  The same source
-is what nvcc compiles for the device (compute-sanitizer is not available on the GPU pool)."""
+"""Memory-safety of the solver source: the warp-level solver is compiled for the host (SIMT emulator)
+with AddressSanitizer + UBSan and run over the shape variants (horizons 2/15/16/32, both layouts,
+models, lane rows, no wrap rows, warm start, RK4, polish, restoration).  The same source is what
+nvcc compiles for the device (compute-sanitizer is not available on the GPU pool)."""
 import os
 import subprocess
 import sys
@@ -21,28 +21,25 @@ emu_util._lib = l
 l.emu_config_default.argtypes = [C.POINTER(MpcrConfig)]
 l.emu_lam_g_stride.argtypes = [C.POINTER(MpcrConfig)]
 l.emu_solve_batch.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
-l.emu_solve_batch_lanes.argtypes = [C.POINTER(MpcrConfig), C.c_int] + [C.c_void_p] * 18
 from emu_util import emu_solve
 from mpc_racing_b200.workload import load_fixture
 d = load_fixture(); d3 = load_fixture("cfg3_t1_triple_512.npz")
-idx = [0, 7]
+idx = [0, 7, 9]
 a = lambda k: d[k][idx]
-for lanes in (False, True):
-    # the warp solver runs through the fiber emulator (slow under ASan): fewer variants
-    for kw in ((dict(), dict(N=32), dict(N=2), dict(N=15), dict(wrap_constraint=0), dict(model=2)) if lanes
-               else (dict(N=32), dict(N=2))):
-        r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), lanes=lanes, trace=True, **kw)
-        assert (r['status'] == 0).all(), (lanes, kw, r['status'])
-    r = emu_solve(d3['x0'][:1], d3['u_prev'][:1], d3['s0'][:1], d3['cx'][:1], d3['cy'][:1],
-                  max_err=d3['max_err'][:1], lane_constraint=1, lanes=lanes)
-    if lanes:
-        r = emu_solve(a('x0'), np.full((2, 2), np.nan), a('s0'), a('cx'), a('cy'), lanes=lanes,
-                      u_warm=np.zeros((2, 2, 30)))
-r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), lanes=True, integrator=1)
-for lanes in (False, True):      # restoration phase
-    r = emu_solve(d3['x0'][[478]], d3['u_prev'][[478]], d3['s0'][[478]], d3['cx'][[478]], d3['cy'][[478]],
-                  max_err=d3['max_err'][[478]], lane_constraint=1, lanes=lanes, restoration=1)
-    assert r['status'][0] == 0
+# the solver runs through the fiber emulator (slow under ASan): few problems per variant
+for kw in (dict(N=32), dict(N=2), dict(N=15, half=True), dict(N=16, half=True, model=2), dict(N=5, wrap_constraint=0)):
+    r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), trace=True, **kw)
+    assert (r['status'] == 0).all(), (kw, r['status'])
+r = emu_solve(d3['x0'][:1], d3['u_prev'][:1], d3['s0'][:1], d3['cx'][:1], d3['cy'][:1],
+              max_err=d3['max_err'][:1], lane_constraint=1)
+r = emu_solve(a('x0'), np.full((3, 2), np.nan), a('s0'), a('cx'), a('cy'), N=10, half=True,
+              u_warm=np.zeros((3, 2, 10)))
+r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), N=8, integrator=1, half=True)
+r = emu_solve(a('x0'), a('u_prev'), a('s0'), a('cx'), a('cy'), N=8, polish_tol=1e-9)
+# restoration phase
+r = emu_solve(d3['x0'][[478]], d3['u_prev'][[478]], d3['s0'][[478]], d3['cx'][[478]], d3['cy'][[478]],
+              max_err=d3['max_err'][[478]], lane_constraint=1, restoration=1)
+assert r['status'][0] == 0
 print("SANITIZED RUN OK")
 '''
 
