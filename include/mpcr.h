@@ -113,6 +113,10 @@ typedef struct mpcr_config {
                               * only to ~1e-3 in flat directions, polished points agree to ~1e-8.  0 = off */
 } mpcr_config;
 
+/* A handle owns one dispatch counter, one set of schedule buffers and one pair of timing events:
+ * calls on the same handle are serialised on the device (a launch on another stream than the
+ * previous one waits for that one), and a handle must not be used from two host threads at once.
+ * Use one handle per stream / thread for concurrent solves. */
 typedef struct mpcr_handle mpcr_handle;
 
 int mpcr_version(void);
@@ -197,6 +201,51 @@ int mpcr_track_lookup_error(mpcr_track* t, int B, const double* s, double lookah
  * BlendedBicycleModel.py:18-58 (model = MPCR_MODEL_*).  x, x_out [B,6]; u [B,2]. */
 int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x, const double* u, double dt,
                     double* x_out, void* cuda_stream);
+
+/* ---- closed-loop control step around the solve (replaces, for R vehicles at once, what the
+ * reference's agent does per simulator tick, agent.py:225-296): two kernels on device-resident
+ * state, so that a receding-horizon step is  prepare -> mpcr_solve_batch -> apply  with no host
+ * work in between (capturable in a CUDA graph).  All pointers are DEVICE pointers owned by the
+ * caller; the handle must have been created with pointers_on_device = 1.
+ *   prepare: [state estimate: yaw rate by finite difference of the yaw with the +-2 pi unwrap,
+ *            velocities world -> body, agent.py:240-254]; progress = projection(X, Y,
+ *            bounds = progress_bound()) (agent.py:80-92, :271); cx, cy = x/y_as_coeffs(progress -
+ *            lookback, lookahead, 4) (agent.py:156-165); lap bookkeeping (travelled distance, lap and
+ *            checkpoint times, largest centerline distance).
+ *   apply:   u = first input of the plan, or (0.5, 0) before start_control_at (agent.py:278-283);
+ *            x = <plant>.step(u, Ts) (models/*.py); failed solves counted; vehicles that finished stay put. */
+typedef struct mpcr_rollout_bufs {
+  int32_t R;                 /* vehicles */
+  int32_t N;                 /* horizon of the plan U [R,2,N] */
+  int32_t n_seg;             /* checkpoint segments (0 = none) */
+  int32_t plant_model;       /* MPCR_MODEL_* of the simulator */
+  int32_t estimate_state;    /* 1: the MPC sees the agent's state estimate instead of the plant state */
+  int32_t start_control_at;  /* control steps with the fixed input (0.5, 0) before the MPC takes over */
+  double Ts, window, lookback, lookahead;   /* agent.py: 0.05, 2.0, 5.0, 45.0 */
+  double target;             /* distance after which a vehicle is finished (laps * length) */
+  double* x;                 /* [R,6] plant state (X, Y, yaw, v_x, v_y, r), updated by apply */
+  double* x_mpc;             /* [R,6] state0 handed to the solve, written by prepare */
+  double* progress;          /* [R] */
+  double* yaw_prev;          /* [R] yaw of the previous tick (state estimate) */
+  double* u_prev;            /* [R,2] input applied at the previous tick */
+  double* cx;                /* [R,5] */
+  double* cy;                /* [R,5] */
+  double* dist;              /* [R] distance to the centerline */
+  int32_t* sign;             /* [R] error_sign */
+  double* travelled;         /* [R] */
+  double* lap_time;          /* [R] NaN until finished */
+  double* max_err;           /* [R] */
+  const double* seg_bounds;  /* [n_seg + 1] cumulative distances of the checkpoints, seg_bounds[0] = 0 */
+  double* seg_t;             /* [R,n_seg] time at which a checkpoint was passed, NaN before */
+  int32_t* steps;            /* [R] control steps taken while not finished */
+  int32_t* fails;            /* [R] failed solves while not finished */
+  int32_t* done;             /* [R] */
+  int32_t* counters;         /* [4]: tick index k, vehicles finished, converged solves of unfinished vehicles, spare */
+} mpcr_rollout_bufs;
+int mpcr_rollout_prepare(mpcr_track* t, const mpcr_rollout_bufs* b, void* cuda_stream);
+/* U [R,2,N] and status [R] of the solve that followed prepare (ignored before start_control_at) */
+int mpcr_rollout_apply(mpcr_handle* h, const mpcr_rollout_bufs* b, const double* U, const int32_t* status,
+                       void* cuda_stream);
 
 /* ---- vehicle-model step with analytic derivatives (replaces CasADi's AD of
  * control/MPC.py:186-260 f_vehicle / f_vehicle_kinematic and of the blend of

@@ -102,3 +102,69 @@ class GeneticAlgorithm:
         best = int(np.argmax(rewards))
         return dict(best_index=best, best_params=decode(self.population[best:best + 1])[0],
                     best_reward=float(rewards[best]), rewards=rewards, rollouts=res)
+
+
+class MultiTrackGA(GeneticAlgorithm):
+    """BASELINE config 5: the population's fitness over SEVERAL tracks, with the (track, individual)
+    rollouts sharded over the ranks of one box (one process per GPU) and only the small fitness
+    table - segment times [tracks x population, checkpoints] - exchanged (one all-gather per
+    generation, NCCL when ``dist`` is an initialised torch.distributed with CUDA tensors).
+
+    ``courses``: list of dicts, one per track: ``ro`` (ClosedLoopRollouts of that track, or None on
+    ranks that own no rollout of it), ``seg_bounds``, ``lap_time_guess``, ``x0`` [6], ``s0``.
+    Rewards follow GA/mpcGA.py:35-48 track by track: every (track, checkpoint) keeps its own
+    running average time, an individual's reward is the sum over tracks and checkpoints.
+    """
+
+    def __init__(self, courses, pop=population_size, seed=1234, rank=0, world=1, dist=None, device=None):
+        self.courses = courses
+        self.rank, self.world, self.dist, self.device = rank, world, dist, device
+        self.n_cp = len(courses[0]["seg_bounds"]) - 1
+        self.avg_times = np.stack([np.full(self.n_cp, c["lap_time_guess"] / self.n_cp) for c in courses])
+        self.rng = np.random.RandomState(seed)
+        self.population = initialize_population(pop, num_parameters, self.rng)
+
+    def evaluate_population(self, max_steps):
+        from ..sharding import shard_range, gather_results
+        P, T = len(self.population), len(self.courses)
+        prm = decode(self.population)
+        lo, hi = shard_range(T * P, self.rank, self.world)           # pair index = track * P + individual
+        seg_local = np.full((hi - lo, self.n_cp), np.nan)
+        fails_local = np.zeros(hi - lo, dtype=np.int32)
+        for t, c in enumerate(self.courses):
+            a, b = max(lo, t * P), min(hi, (t + 1) * P)
+            if a >= b:
+                continue
+            ind = np.arange(a - t * P, b - t * P)
+            res = c["ro"].run(np.repeat(np.asarray(c["x0"])[None], len(ind), 0), np.repeat(c["s0"], len(ind)),
+                              params=prm[ind], max_steps=max_steps, seg_bounds=c["seg_bounds"])
+            seg_local[a - lo:b - lo] = res["seg_times"]
+            fails_local[a - lo:b - lo] = res["fail_steps"]
+        full = gather_results(dict(seg=seg_local, fails=fails_local), T * P, self.rank, self.world, self.dist,
+                              self.device)
+        seg = full["seg"].reshape(T, P, self.n_cp)
+        rewards = np.zeros(P)
+        for t in range(T):
+            for i in range(P):
+                for cpt in range(self.n_cp):
+                    if np.isnan(seg[t, i, cpt]):
+                        continue                                   # unfinished segment: no reward
+                    average_time = self.avg_times[t, cpt]
+                    self.avg_times[t, cpt] = compute_avg_time(seg[t, i, cpt], average_time)
+                    rewards[i] += compute_reward(seg[t, i, cpt], average_time)
+        return rewards, dict(seg_times=seg, fail_steps=full["fails"].reshape(T, P))
+
+    def run_step(self, max_steps=400):
+        rewards, res = self.evaluate_population(max_steps)
+        # every rank holds the same rewards and the same random stream: identical populations afterwards
+        p1, p2 = self.select_parents(rewards)
+        if self.rng.rand() < crossover_rate:
+            c1, c2 = self.crossover(p1, p2)
+        else:
+            c1, c2 = p1.copy(), p2.copy()
+        worst = np.argsort(rewards)[:2]
+        self.population[worst[0]] = self.mutate(c1)
+        self.population[worst[1]] = self.mutate(c2)
+        best = int(np.argmax(rewards))
+        return dict(best_index=best, best_params=decode(self.population[best:best + 1])[0],
+                    best_reward=float(rewards[best]), rewards=rewards, rollouts=res)

@@ -47,7 +47,23 @@ EXPORTED_SYMBOLS = [
     "mpcr_launch_info", "mpcr_last_launch_count", "mpcr_fp64_peak_tflops",
     "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
     "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step", "mpcr_model_eval",
+    "mpcr_rollout_prepare", "mpcr_rollout_apply",
 ]
+
+
+class MpcrRolloutBufs(C.Structure):
+    """Mirror of ``struct mpcr_rollout_bufs`` (include/mpcr.h): device pointers as raw addresses."""
+    _fields_ = [
+        ("R", C.c_int32), ("N", C.c_int32), ("n_seg", C.c_int32), ("plant_model", C.c_int32),
+        ("estimate_state", C.c_int32), ("start_control_at", C.c_int32),
+        ("Ts", C.c_double), ("window", C.c_double), ("lookback", C.c_double), ("lookahead", C.c_double),
+        ("target", C.c_double),
+        ("x", C.c_void_p), ("x_mpc", C.c_void_p), ("progress", C.c_void_p), ("yaw_prev", C.c_void_p),
+        ("u_prev", C.c_void_p), ("cx", C.c_void_p), ("cy", C.c_void_p), ("dist", C.c_void_p),
+        ("sign", C.c_void_p), ("travelled", C.c_void_p), ("lap_time", C.c_void_p), ("max_err", C.c_void_p),
+        ("seg_bounds", C.c_void_p), ("seg_t", C.c_void_p), ("steps", C.c_void_p), ("fails", C.c_void_p),
+        ("done", C.c_void_p), ("counters", C.c_void_p),
+    ]
 
 _lib = None
 
@@ -107,6 +123,10 @@ def load_library(path=None):
     lib.mpcr_plant_step.restype = C.c_int
     lib.mpcr_model_eval.argtypes = [V, C.c_int, C.c_int, C.c_int, V, V, C.c_double, V, V, V, V, V]
     lib.mpcr_model_eval.restype = C.c_int
+    lib.mpcr_rollout_prepare.argtypes = [V, C.POINTER(MpcrRolloutBufs), V]
+    lib.mpcr_rollout_prepare.restype = C.c_int
+    lib.mpcr_rollout_apply.argtypes = [V, C.POINTER(MpcrRolloutBufs), V, V, V]
+    lib.mpcr_rollout_apply.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

@@ -281,7 +281,12 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
                         int trace_rows, cudaStream_t st) {
   // The handle's dispatch counter, order buffers and timing events are shared by all of its
   // launches: a launch on another stream than the previous one waits for that one first.
-  if (h->launched) CK(cudaStreamWaitEvent(st, h->ev_done, 0));
+  // Inside a stream capture (CUDA graph of a closed-loop step) the launches are ordered by the graph
+  // and the timing events are left out.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CK(cudaStreamIsCapturing(st, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (h->launched && !capturing) CK(cudaStreamWaitEvent(st, h->ev_done, 0));
   const bool use_half = h->half.kernel != nullptr &&
                         (h->kernel_sel == MPCR_KERNEL_HALFWARP ||
                          (h->kernel_sel == MPCR_KERNEL_AUTO && B > h->num_sms * h->warp.blocks_per_sm));
@@ -320,7 +325,7 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
     h->order_cap = B;
   }
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
-  CK(cudaEventRecord(h->ev0, st));          // the schedule kernels are inside the timed region
+  if (!capturing) CK(cudaEventRecord(h->ev0, st));          // the schedule kernels are inside the timed region
   const int* order = nullptr;
   h->last_launches = 1;
   if (sched) {
@@ -335,10 +340,12 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
   }
   L.kernel<<<grid, 32, L.smem_bytes, st>>>(h->cfg, in, out, B, trace_rows, h->d_counter, order);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, st));
-  CK(cudaEventRecord(h->ev_done, st));
-  h->launched = true;
-  h->timed = true;
+  if (!capturing) {
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaEventRecord(h->ev_done, st));
+    h->launched = true;
+    h->timed = true;
+  }
   return MPCR_OK;
 }
 
@@ -807,6 +814,162 @@ extern "C" int mpcr_plant_step(mpcr_handle* h, int model, int B, const double* x
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d);
   if (e != cudaSuccess) { h->err = std::string("mpcr_plant_step: ") + cudaGetErrorString(e); return MPCR_ERR_CUDA; }
+  return MPCR_OK;
+}
+
+// =====================================================================================
+// Closed-loop control step around the solve: prepare (estimate, project, refit, bookkeeping) and
+// apply (first input of the plan -> plant step) on device-resident state, one thread per vehicle.
+// =====================================================================================
+namespace mpcr {
+
+template <bool STAGED>
+__global__ void __launch_bounds__(128) rollout_prepare_kernel(const TrackDev dev, const mpcr_rollout_bufs b) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  __shared__ __align__(8) unsigned long long bar;
+  const double* base = dev.table;
+  if (STAGED) {
+    tma_stage(tsm, dev.table, (unsigned)dev.bytes, &bar);
+    base = reinterpret_cast<const double*>(tsm);
+  }
+  const TrackView t = make_view(dev, base);
+  const int k = b.counters[0];
+  const double L = t.length;
+  int newly_done = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.R; r += gridDim.x * blockDim.x) {
+    double x[6];
+    for (int a = 0; a < 6; ++a) x[a] = b.x[(size_t)r * 6 + a];
+    // ---- what the MPC sees (agent.py:240-254) ------------------------------------------------
+    double xe[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+    if (b.estimate_state) {
+      const double yaw = x[2];
+      // world velocity of the plant, rotated back into the vehicle frame by the agent
+      const double wx = x[3] * cos(yaw) - x[4] * sin(yaw), wy = x[3] * sin(yaw) + x[4] * cos(yaw);
+      xe[3] = wx * cos(-yaw) - wy * sin(-yaw);
+      xe[4] = wx * sin(-yaw) + wy * cos(-yaw);
+      if (k > 0) {
+        const double old = b.yaw_prev[r];
+        double d;
+        if (yaw - old > 3.0) d = yaw - (old + 3.141592653589793 * 2);
+        else if (yaw - old < -3.0) d = yaw - (old - 3.141592653589793 * 2);
+        else d = yaw - old;
+        xe[5] = d / b.Ts;
+      }
+      b.yaw_prev[r] = yaw;
+    }
+    for (int a = 0; a < 6; ++a) b.x_mpc[(size_t)r * 6 + a] = xe[a];
+    // ---- progress = projection(X, Y, bounds = progress_bound()) (agent.py:80-92, :271) -------
+    const double p_old = b.progress[r];
+    const double lo = py_mod(p_old - b.window, L), hi = py_mod(p_old + b.window, L);
+    double s_new, d;
+    track_project(t, x[0], x[1], fmin(lo, hi), fmax(lo, hi), &s_new, &d);   // swapped at the wrap -> global search
+    b.progress[r] = s_new;
+    b.dist[r] = d;
+    b.sign[r] = track_error_sign(t, x[0], x[1], s_new);
+    // ---- reference path of the horizon (agent.py:156-165) ------------------------------------
+    double cx[5], cy[5];
+    track_fit4(t, s_new - b.lookback, b.lookahead, cx, cy);
+    for (int a = 0; a < 5; ++a) { b.cx[(size_t)r * 5 + a] = cx[a]; b.cy[(size_t)r * 5 + a] = cy[a]; }
+    // ---- lap bookkeeping -----------------------------------------------------------------------
+    if (!b.done[r]) {
+      double tr = b.travelled[r];
+      if (k > 0) tr += py_mod(s_new - p_old + 0.5 * L, L) - 0.5 * L;
+      b.travelled[r] = tr;
+      b.max_err[r] = fmax(b.max_err[r], d);
+      for (int j = 0; j < b.n_seg; ++j) {
+        double* st = b.seg_t + (size_t)r * b.n_seg + j;
+        if (*st != *st && tr >= b.seg_bounds[j + 1] - 1e-12) *st = k * b.Ts;
+      }
+      if (tr >= b.target) {
+        b.lap_time[r] = k * b.Ts;
+        b.done[r] = 1;
+        newly_done++;
+      }
+    }
+  }
+  if (newly_done) atomicAdd(&b.counters[1], newly_done);
+}
+
+__global__ void __launch_bounds__(128) rollout_apply_kernel(const mpcr_rollout_bufs b, const double* __restrict__ U,
+                                                            const int32_t* __restrict__ status) {
+  const int k = b.counters[0];
+  const bool mpc = k >= b.start_control_at;
+  int conv = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.R; r += gridDim.x * blockDim.x) {
+    double u[2] = {0.5, 0.0};                                  // agent.py:283
+    if (mpc) { u[0] = U[(size_t)r * 2 * b.N]; u[1] = U[(size_t)r * 2 * b.N + b.N]; }
+    b.u_prev[(size_t)r * 2] = u[0];
+    b.u_prev[(size_t)r * 2 + 1] = u[1];
+    if (b.done[r]) continue;
+    double x[6], o[6];
+    for (int a = 0; a < 6; ++a) x[a] = b.x[(size_t)r * 6 + a];
+    plant_step(b.plant_model, x, u, b.Ts, o);
+    for (int a = 0; a < 6; ++a) b.x[(size_t)r * 6 + a] = o[a];
+    b.steps[r] += 1;
+    if (mpc) {
+      if (status[r] < 0) b.fails[r] += 1;
+      else conv++;
+    }
+  }
+  if (conv) atomicAdd(&b.counters[2], conv);
+  __syncthreads();
+  // the tick counter moves when the last block is through (every block read k at its start; the
+  // next kernel on the stream starts after this one has finished)
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(&b.counters[3], 1) + 1;
+    if (arrived == (int)gridDim.x) {
+      b.counters[3] = 0;
+      b.counters[0] = k + 1;
+    }
+  }
+}
+}  // namespace mpcr
+
+static bool rollout_bufs_ok(const mpcr_rollout_bufs* b) {
+  return b && b->R >= 0 && b->N >= 1 && b->n_seg >= 0 && b->plant_model >= 0 && b->plant_model <= 2 &&
+         b->Ts > 0.0 && b->x && b->x_mpc && b->progress && b->yaw_prev && b->u_prev && b->cx && b->cy &&
+         b->dist && b->sign && b->travelled && b->lap_time && b->max_err && b->steps && b->fails && b->done &&
+         b->counters && (b->n_seg == 0 || (b->seg_bounds && b->seg_t));
+}
+
+extern "C" int mpcr_rollout_prepare(mpcr_track* t, const mpcr_rollout_bufs* b, void* stream) {
+  if (!t) return MPCR_ERR_INVALID_ARG;
+  mpcr_handle* h = t->h;
+  if (!rollout_bufs_ok(b) || !h->pub.pointers_on_device) {
+    h->err = "mpcr_rollout_prepare: invalid buffers (device pointers, handle with pointers_on_device = 1)";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  if (b->R == 0) return MPCR_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 128;
+  int blocks = (b->R + threads - 1) / threads;
+  if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
+  if (t->staged) {
+    CK(cudaFuncSetAttribute(rollout_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)t->dev.bytes));
+    rollout_prepare_kernel<true><<<blocks, threads, t->dev.bytes, st>>>(t->dev, *b);
+  } else {
+    rollout_prepare_kernel<false><<<blocks, threads, 0, st>>>(t->dev, *b);
+  }
+  CK(cudaGetLastError());
+  return MPCR_OK;
+}
+
+extern "C" int mpcr_rollout_apply(mpcr_handle* h, const mpcr_rollout_bufs* b, const double* U,
+                                  const int32_t* status, void* stream) {
+  if (!h) return MPCR_ERR_INVALID_ARG;
+  if (!rollout_bufs_ok(b) || !U || !status || !h->pub.pointers_on_device) {
+    h->err = "mpcr_rollout_apply: invalid buffers (device pointers, handle with pointers_on_device = 1)";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  if (b->R == 0) return MPCR_OK;
+  CK(cudaSetDevice(h->device));
+  const int threads = 128;
+  int blocks = (b->R + threads - 1) / threads;
+  if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+  rollout_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*b, U, status);
+  CK(cudaGetLastError());
   return MPCR_OK;
 }
 

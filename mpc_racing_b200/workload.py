@@ -1,7 +1,8 @@
-"""Synthetic problem batches for tests and bench.
+"""Synthetic problem batches for tests, smoke() and bench.
 
 The start states of config 2 were sampled with the reference's own spline code
-(tests/golden/make_golden.py, seed 1234) and are committed as a fixture; larger
+(tests/golden/make_golden.py, seed 1234) and are committed as fixtures inside the package
+(mpc_racing_b200/data/fixtures: an installed package needs no tests/ tree); larger
 batches are built from them by seeded perturbations of the vehicle state so that
 every problem in a batch is distinct.
 """
@@ -9,7 +10,7 @@ import os
 
 import numpy as np
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "fixtures")
 
 
 def load_fixture(name="cfg2_shanghai_4096.npz"):

@@ -14,6 +14,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# problem-input fixtures live inside the package (bench.py and smoke() use them too)
+FIX = os.path.join(HERE, "..", "..", "mpc_racing_b200", "data", "fixtures")
 REF = "/root/reference"
 SEED = 1234      # the harness's default seed (automatic_control_GRAIC.py:928-930)
 
@@ -56,7 +58,7 @@ def make_problems():
     cl = ParameterizedCenterline("shanghai_intl_circuit")
     rng = np.random.default_rng(SEED)
     d = sample_problems(cl, 4096, rng)
-    np.savez_compressed(os.path.join(HERE, "cfg2_shanghai_4096.npz"), **d)
+    np.savez_compressed(os.path.join(FIX, "cfg2_shanghai_4096.npz"), **d)
     # config 1: script/test_mpc.py:18-51 verbatim
     s0 = 69.6
     cfg1 = dict(x0=np.array([[171, 91.8, -0.219, 20, 0.48, -0.059]], dtype=np.float64),
@@ -65,15 +67,15 @@ def make_problems():
                 cy=np.array([cl.y_as_coeffs(s0 - 5, 75, deg=4)]),
                 max_err=np.array([cl.lookup_error(s0, 75) - 1.85 / 2]),
                 Ts=np.array([0.1]), N=np.array([25]))
-    np.savez_compressed(os.path.join(HERE, "cfg1_test_mpc.npz"), **cfg1)
+    np.savez_compressed(os.path.join(FIX, "cfg1_test_mpc.npz"), **cfg1)
     # config 3 inputs: t1_triple with lane bounds
     cl = ParameterizedCenterline("t1_triple")
     d = sample_problems(cl, 512, np.random.default_rng(SEED + 3))
-    np.savez_compressed(os.path.join(HERE, "cfg3_t1_triple_512.npz"), **d)
+    np.savez_compressed(os.path.join(FIX, "cfg3_t1_triple_512.npz"), **d)
     # production settings (agent.py:139-181): N = 15, lookahead 45, on t4
     cl = ParameterizedCenterline("t4")
     d = sample_problems(cl, 256, np.random.default_rng(SEED + 4), lookahead=45.0)
-    np.savez_compressed(os.path.join(HERE, "prod_t4_256.npz"), **d)
+    np.savez_compressed(os.path.join(FIX, "prod_t4_256.npz"), **d)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ from oracle import cxx, vehicle as V
 from parity_util import oracle_solve
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mpc_racing_b200", "data", "fixtures")
 
 
 def test_bunch_kaufman_solve_and_inertia():
@@ -63,7 +64,7 @@ def test_live_against_numpy_oracle(case):
     """Same problems through oracle/ipm.py (live) and the C++ oracle: same status, iteration count
     within one, objective to 1e-8, inputs to 1e-6."""
     name = "cfg3_t1_triple_512" if case.startswith("lane") else "cfg2_shanghai_4096"
-    d = np.load(os.path.join(G, name + ".npz"))
+    d = np.load(os.path.join(FIX, name + ".npz"))
     idx = [0, 3] if case != "lane+resto" else [5, 21]
     kw_np, kw_cx, opts, N = {}, {}, None, 30
     if case == "kinematic":
@@ -98,7 +99,7 @@ def test_live_against_numpy_oracle(case):
 
 
 def test_dense_and_block_tridiagonal_linear_algebra_agree():
-    d = np.load(os.path.join(G, "cfg2_shanghai_4096.npz"))
+    d = np.load(os.path.join(FIX, "cfg2_shanghai_4096.npz"))
     sl = slice(0, 16)
     a = cxx.solve_batch(d["x0"][sl], d["u_prev"][sl], d["s0"][sl], d["cx"][sl], d["cy"][sl], linsol="blocktri")
     b = cxx.solve_batch(d["x0"][sl], d["u_prev"][sl], d["s0"][sl], d["cx"][sl], d["cy"][sl], linsol="dense")
@@ -116,7 +117,7 @@ def test_dense_and_block_tridiagonal_linear_algebra_agree():
 def test_whole_batches_against_numpy_oracle_golden(name, gold, kw, N):
     """EVERY problem of the fixture batches: the committed numpy-oracle solutions
     (tests/golden/*_oracle.npz, generator make_oracle_solutions.py) against the C++ oracle."""
-    d = np.load(os.path.join(G, name + ".npz"))
+    d = np.load(os.path.join(FIX, name + ".npz"))
     g = np.load(os.path.join(G, gold + ".npz"))
     r = cxx.solve_batch(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"], N=N, max_err=d["max_err"], **kw)
     assert (r["status"] == g["status"]).all()
@@ -130,7 +131,7 @@ def test_whole_batches_against_numpy_oracle_golden(name, gold, kw, N):
 
 
 def test_polish_keeps_status_and_tightens():
-    d = np.load(os.path.join(G, "cfg2_shanghai_4096.npz"))
+    d = np.load(os.path.join(FIX, "cfg2_shanghai_4096.npz"))
     sl = slice(0, 32)
     a = cxx.solve_batch(d["x0"][sl], d["u_prev"][sl], d["s0"][sl], d["cx"][sl], d["cy"][sl])
     p = cxx.solve_batch(d["x0"][sl], d["u_prev"][sl], d["s0"][sl], d["cx"][sl], d["cy"][sl], polish_tol=1e-9)

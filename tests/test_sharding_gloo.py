@@ -63,3 +63,57 @@ def test_two_rank_gloo_matches_single_process():
     np.testing.assert_array_equal(full["iters"], ref["iters"])
     np.testing.assert_array_equal(full["obj"], ref["obj"])
     np.testing.assert_array_equal(full["u0"], ref["U"][:, :, 0])
+
+
+# ---- config 5: the GA's (track, individual) rollouts sharded over ranks, fitness table gathered -----
+class _FakeRollouts:
+    """Stands in for ClosedLoopRollouts on the CPU: deterministic segment times from the parameters."""
+
+    def __init__(self, track_id):
+        self.track_id = track_id
+
+    def run(self, x0, s0, params=None, max_steps=0, seg_bounds=None):
+        n_cp = len(seg_bounds) - 1
+        base = 5.0 + 0.1 * self.track_id + 1e-4 * params[:, 0] + params[:, 1]
+        seg = base[:, None] + 0.05 * np.arange(n_cp)[None, :]
+        seg[params[:, 3] == 4.0, -1] = np.nan          # some individuals do not finish the last segment
+        return dict(seg_times=seg, fail_steps=np.zeros(len(params), dtype=np.int32))
+
+
+def _ga(rank, world, dist):
+    from mpc_racing_b200.GA import mpcGA
+    courses = [dict(ro=_FakeRollouts(t), seg_bounds=[0, 10, 20, 30], lap_time_guess=18.0, x0=np.zeros(6), s0=0.0)
+               for t in range(5)]
+    ga = mpcGA.MultiTrackGA(courses, pop=13, seed=5, rank=rank, world=world, dist=dist)
+    out = [ga.run_step(max_steps=10) for _ in range(3)]
+    return ga.population.copy(), np.stack([o["rewards"] for o in out]), ga.avg_times.copy()
+
+
+def _ga_worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pop, rewards, avg = _ga(rank, world, dist)
+    q.put((rank, pop, rewards, avg))
+    dist.destroy_process_group()
+
+
+def test_multitrack_ga_sharded_over_two_ranks_equals_one_rank():
+    pop1, rew1, avg1 = _ga(0, 1, None)
+    assert rew1.shape == (3, 13) and (rew1 > 0).all()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ga_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, pop, rew, avg in got:          # every rank ends with the single-process population
+        np.testing.assert_array_equal(pop, pop1)
+        np.testing.assert_array_equal(rew, rew1)
+        np.testing.assert_array_equal(avg, avg1)

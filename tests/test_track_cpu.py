@@ -132,3 +132,32 @@ def test_plant_device_functions_match_reference(lib):
         out = np.empty_like(x0)
         lib.emu_plant_step(mid, len(x0), _p(x0), _p(u), _p(dt), _p(out))
         np.testing.assert_allclose(out, g[name], rtol=1e-13, atol=1e-12)
+
+
+def test_track_segments_reproduce_the_reference_quad_and_fsolve_values():
+    """splines/TrackSegments.py:8-35 with the reference's own recipe (scipy quad + fsolve) over this
+    package's spline table: lap time and checkpoint bounds of the reference golden to 1e-9 (the
+    Simpson-table variant converges to the exact integral instead, ~1e-4 away from QUADPACK's value)."""
+    import warnings
+    from mpc_racing_b200.splines import tables
+    from mpc_racing_b200.splines.TrackSegments import TrackSegments
+    from mpc_racing_b200.splines.util import euclidean, midpoint
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "splines_golden.npz"))
+
+    class HostLine:          # the host part of ParameterizedCenterline (no device needed for the precompute)
+        pass
+    for t in ("t1_triple", "t4"):
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mpc_racing_b200", "data",
+                                 "tracks", t + ".npz"))
+        wp = [tuple(p) for p in d["waypoints"]]
+        if euclidean(wp[-1], wp[0]) > 0.1:
+            wp = wp + [midpoint(wp[-1], wp[0], alpha=0.9)]
+        line = HostLine()
+        line._tables = tables.line_tables(wp)
+        line.length = line._tables["length"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # QUADPACK's round-off warning, as in the reference
+            seg = TrackSegments(line, 5, 30, 1500, 1500, 250)
+        gold = g[f"{t}/segments"]
+        assert abs(seg.lap_time - gold[0]) <= 1e-9 * gold[0]
+        np.testing.assert_allclose(seg.bounds, gold[1:], rtol=1e-9, atol=1e-9)
