@@ -138,16 +138,23 @@ def _numpy_one(args):
 
 
 def numpy_oracle_rate(batch, n, cores, N):
-    """Context figure: the numpy oracle (oracle/ipm.py) in a process pool."""
+    """Context figure: the numpy oracle (oracle/ipm.py) in a process pool.  "spawn": this process has
+    live CUDA and OpenMP runtimes, neither survives a fork."""
     from multiprocessing import get_context
+    env = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     jobs = [(batch["x0"][b], batch["u_prev"][b], batch["s0"][b], batch["cx"][b], batch["cy"][b], N) for b in range(n)]
-    with get_context("fork").Pool(cores) as pool:
+    with get_context("spawn").Pool(cores) as pool:
         pool.map(_numpy_one, jobs[:cores])
         t0 = time.perf_counter()
         st = pool.map(_numpy_one, jobs, chunksize=1)
         dt = time.perf_counter() - t0
+    for k, v in env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     return sum(1 for s in st if s >= 0) / dt
 
 
@@ -522,18 +529,25 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
     fit_local = None
 
     def one_step(state_in_hbm):
-        """K control steps of every rollout of this rank.  Returns (converged solves, fitness vector)."""
+        """K control steps of every rollout of this rank; the tracks' engines run concurrently, each on
+        its own stream.  Returns (converged solves, fitness vector)."""
         conv = 0
         fit = []
+        sess = []
         for e in engines:
+            s = e["sess"] if state_in_hbm else e["ro"].begin(e["x0"], e["s0"], params=e["prm"])   # H2D of the start states
+            e["c0"] = e["ro"].converged_so_far(s)
+            e["ro"].advance(s, K, sync=False)
+            sess.append(s)
+        for e, s in zip(engines, sess):
             if state_in_hbm:
-                r = e["ro"].advance(e["sess"], K)
+                e["ro"].stream.synchronize()
+                conv += e["ro"].converged_so_far(s) - e["c0"]
+                fit.append(s.travelled)
             else:
-                sess = e["ro"].begin(e["x0"], e["s0"], params=e["prm"])      # H2D of the start states
-                r = e["ro"].advance(sess, K)
-                r = e["ro"].fetch(sess)                                       # D2H of the result
-            conv += r["converged_solves"]
-            fit.append(r["travelled"])
+                r = e["ro"].fetch(s)                                          # D2H of the result
+                conv += r["converged_solves"] - e["c0"]
+                fit.append(r["travelled"])
         return conv, fit
 
     for e in engines:
@@ -619,7 +633,7 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
-                     "traffic": None, "kernel": "mpcr::solve_kernel (half-warp layout)",
+                     "traffic": None, "kernel": "mpcr::solve_kernel",
                      "kernel_ms": solve_ms,
                      "note": "iteration counts are not read back inside the loop; see the cfg2 line for the roofline"},
         "ranks": ranks,

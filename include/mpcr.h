@@ -41,13 +41,11 @@ extern "C" {
 #define MPCR_MODEL_KINEMATIC 1
 #define MPCR_MODEL_BLENDED 2
 
-/* solve-kernel layouts: one problem per warp (lane k = stage k, any horizon up to 32) or two
- * problems per warp (one per half-warp, horizons up to 16: the production horizon 15 leaves 17 of
- * 32 lanes idle otherwise).  AUTO = HALFWARP when N <= 16 and the batch has more than one problem,
- * else WARP.  Results do not depend on the layout. */
+/* solve-kernel layout: one problem per warp (lane k = stage k).  AUTO = WARP; the field is kept for
+ * further layouts (round 2 measured "two problems per warp" for horizons up to 16: the two half-
+ * warps run as divergent paths of one warp and gain nothing). */
 #define MPCR_KERNEL_AUTO 0
 #define MPCR_KERNEL_WARP 1
-#define MPCR_KERNEL_HALFWARP 2
 
 /* integrators of the NLP's dynamics rows (also used by mpcr_model_eval) */
 #define MPCR_INTEGRATOR_EULER 0

@@ -77,7 +77,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MPCR_LIB") or LIB_PATH       # MPCR_LIB: development builds side by side
     if not os.path.exists(p):
         raise MpcrError(
             f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "

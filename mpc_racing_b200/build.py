@@ -1,6 +1,6 @@
 """In-tree build of libmpcr.so (nvcc, sm_100a only).
 
-The solve kernel has 8 template variants (restoration x integrator x layout); each is its own
+The solve kernel has 4 template variants (restoration x integrator, three models each); each is its own
 translation unit (csrc/mpcr_solve_variant.cu with -D flags) so that they compile in parallel.
 """
 import os
@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmpcr.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-VARIANTS = [(r, i, h) for r in (0, 1) for i in (0, 1) for h in (0, 1)]
+VARIANTS = [(r, i) for r in (0, 1) for i in (0, 1)]
 
 
 def _deps():
@@ -25,9 +25,9 @@ def _deps():
 def units():
     """(object name, source, extra flags) of every translation unit."""
     u = [("mpcr.o", os.path.join(CSRC, "mpcr.cu"), [])]
-    for r, i, h in VARIANTS:
-        u.append((f"solve_r{r}i{i}h{h}.o", os.path.join(CSRC, "mpcr_solve_variant.cu"),
-                  [f"-DMPCR_V_RESTO={r}", f"-DMPCR_V_IG={i}", f"-DMPCR_V_HALF={h}"]))
+    for r, i in VARIANTS:
+        u.append((f"solve_r{r}i{i}.o", os.path.join(CSRC, "mpcr_solve_variant.cu"),
+                  [f"-DMPCR_V_RESTO={r}", f"-DMPCR_V_IG={i}"]))
     return u
 
 

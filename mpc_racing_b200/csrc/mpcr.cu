@@ -4,9 +4,9 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 //
 // Solve kernel (mpcr_solve_variant.cu, one translation unit per template variant): persistent,
-// one warp (= one block of 32 threads) per problem - or per two problems when the horizon fits a
-// half-warp; problems handed out through an atomic counter so that converged problems free
-// their lanes immediately.  No tensor cores (9x9 / 3x3 fp64 blocks), no CPU path.
+// one warp (= one block of 32 threads) per problem, problems handed out through an atomic counter
+// so that converged problems free their warp immediately.  No tensor cores (9x9 / 3x3 fp64
+// blocks), no CPU path.
 #include <cuda_runtime.h>
 
 #include <stdlib.h>
@@ -23,22 +23,14 @@
 
 namespace mpcr {
 
-template <> SolveKernelFn solve_kernel_table<false, 0, false>(int);
-template <> SolveKernelFn solve_kernel_table<false, 0, true>(int);
-template <> SolveKernelFn solve_kernel_table<false, 1, false>(int);
-template <> SolveKernelFn solve_kernel_table<false, 1, true>(int);
-template <> SolveKernelFn solve_kernel_table<true, 0, false>(int);
-template <> SolveKernelFn solve_kernel_table<true, 0, true>(int);
-template <> SolveKernelFn solve_kernel_table<true, 1, false>(int);
-template <> SolveKernelFn solve_kernel_table<true, 1, true>(int);
+template <> SolveKernelFn solve_kernel_table<false, 0>(int);
+template <> SolveKernelFn solve_kernel_table<false, 1>(int);
+template <> SolveKernelFn solve_kernel_table<true, 0>(int);
+template <> SolveKernelFn solve_kernel_table<true, 1>(int);
 
-SolveKernelFn solve_kernel_variant(int model, bool resto, int ig, bool half) {
-  if (resto) {
-    if (ig) return half ? solve_kernel_table<true, 1, true>(model) : solve_kernel_table<true, 1, false>(model);
-    return half ? solve_kernel_table<true, 0, true>(model) : solve_kernel_table<true, 0, false>(model);
-  }
-  if (ig) return half ? solve_kernel_table<false, 1, true>(model) : solve_kernel_table<false, 1, false>(model);
-  return half ? solve_kernel_table<false, 0, true>(model) : solve_kernel_table<false, 0, false>(model);
+SolveKernelFn solve_kernel_variant(int model, bool resto, int ig) {
+  if (resto) return ig ? solve_kernel_table<true, 1>(model) : solve_kernel_table<true, 0>(model);
+  return ig ? solve_kernel_table<false, 1>(model) : solve_kernel_table<false, 0>(model);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -132,15 +124,11 @@ struct mpcr_handle {
   int device = 0;
   int num_sms = 0;
   int* d_counter = nullptr;
-  // layout: one problem per warp (any N <= 32) or two per warp (N <= 16); AUTO picks the half-warp
-  // layout when it fits and the batch has more problems than the GPU holds warps (a problem that
-  // can have a warp of its own is solved faster there)
-  struct Layout {
+  struct Layout {                        // the solve kernel of this handle (model, restoration, integrator)
     SolveKernelFn kernel = nullptr;
     int smem_bytes = 0;
     int blocks_per_sm = 0;
-  } warp, half;
-  int kernel_sel = MPCR_KERNEL_AUTO;     // config / MPCR_KERNEL env
+  } warp;
   cudaEvent_t ev_done = nullptr;         // end of the last launch: orders launches from different streams
   bool launched = false;
   int last_blocks = 0, last_smem = 0;    // geometry of the last launch
@@ -192,12 +180,6 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
-  h->kernel_sel = cfg->solve_kernel;
-  {
-    const char* e = getenv("MPCR_KERNEL");
-    if (e && !strcmp(e, "warp")) h->kernel_sel = MPCR_KERNEL_WARP;
-    if (e && !strcmp(e, "half") && h->cfg.N <= 16) h->kernel_sel = MPCR_KERNEL_HALFWARP;
-  }
   h->schedule = cfg->schedule;
   {
     const char* e = getenv("MPCR_SCHEDULE");
@@ -211,11 +193,10 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
   }
   const bool resto = h->cfg.o.restoration != 0;
   const int ig = h->cfg.integrator;
-  for (int half = 0; half < 2; ++half) {
-    if (half && h->cfg.N > 16) break;
-    mpcr_handle::Layout& L = half ? h->half : h->warp;
-    L.kernel = solve_kernel_variant(h->cfg.model, resto, ig, half != 0);
-    L.smem_bytes = (half ? 2 : 1) * ws_doubles(h->cfg.N, ig) * (int)sizeof(double);
+  {
+    mpcr_handle::Layout& L = h->warp;
+    L.kernel = solve_kernel_variant(h->cfg.model, resto, ig);
+    L.smem_bytes = ws_doubles(h->cfg.N, ig) * (int)sizeof(double);
     CK(cudaFuncSetAttribute(L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     h->carve_now = h->carve_env > 0 ? h->carve_env : (int)cudaSharedmemCarveoutMaxShared;
     CK(cudaFuncSetAttribute(L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carve_now));
@@ -287,14 +268,9 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
   CK(cudaStreamIsCapturing(st, &cap));
   const bool capturing = cap != cudaStreamCaptureStatusNone;
   if (h->launched && !capturing) CK(cudaStreamWaitEvent(st, h->ev_done, 0));
-  const bool use_half = h->half.kernel != nullptr &&
-                        (h->kernel_sel == MPCR_KERNEL_HALFWARP ||
-                         (h->kernel_sel == MPCR_KERNEL_AUTO && B > h->num_sms * h->warp.blocks_per_sm));
-  const mpcr_handle::Layout& L = use_half ? h->half : h->warp;
-  const int per_block = use_half ? 2 : 1;
+  const mpcr_handle::Layout& L = h->warp;
   int grid = h->num_sms * L.blocks_per_sm;
-  const int need = (B + per_block - 1) / per_block;
-  if (grid > need) grid = need;
+  if (grid > B) grid = B;
   h->last_blocks = grid;
   h->last_smem = L.smem_bytes;
   if (h->carve_env < 0) {
@@ -313,7 +289,7 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
     h->carve_now = carve;
   }
   const bool sched = h->schedule == MPCR_SCHEDULE_CURVATURE ||
-                     (h->schedule == MPCR_SCHEDULE_AUTO && B > grid * per_block);
+                     (h->schedule == MPCR_SCHEDULE_AUTO && B > grid);
   if (sched && B > h->order_cap) {
     if (h->d_order) cudaFree(h->d_order);
     if (h->d_bin) cudaFree(h->d_bin);

@@ -25,26 +25,20 @@ namespace mpcr {
 // ---------------------------------------------------------------------------
 // warp primitives
 // ---------------------------------------------------------------------------
-// Every collective takes the participation mask of the calling problem: the full warp, or one
-// half of it when two problems share a warp (HALF, horizons up to 16) - the two halves then run
-// as independent lock-step groups of 16 lanes (disjoint masks).  `src` is an absolute lane id.
-constexpr unsigned kFullMask = 0xffffffffu;
 #if defined(MPCR_EMU)
 MPCR_D int lane_id() { return emu::lane(); }
-MPCR_D double shfl(unsigned, double v, int src) { return emu::shfl_f64(v, src); }
-MPCR_D int shfl_i(unsigned, int v, int src) { return emu::shfl_i32(v, src); }
-MPCR_D void syncwarp(unsigned) { emu::syncwarp(); }
-MPCR_D double shfl_xor(unsigned, double v, int m) { return emu::shfl_f64(v, emu::lane() ^ m); }
-MPCR_D int shfl_xor_i(unsigned, int v, int m) { return emu::shfl_i32(v, emu::lane() ^ m); }
-MPCR_D int atomic_next(int* counter) { return (*counter)++; }
+MPCR_D double shfl(double v, int src) { return emu::shfl_f64(v, src); }
+MPCR_D int shfl_i(int v, int src) { return emu::shfl_i32(v, src); }
+MPCR_D void syncwarp() { emu::syncwarp(); }
+MPCR_D double shfl_xor(double v, int m) { return emu::shfl_f64(v, emu::lane() ^ m); }
+MPCR_D int shfl_xor_i(int v, int m) { return emu::shfl_i32(v, emu::lane() ^ m); }
 #else
 MPCR_D int lane_id() { return threadIdx.x & 31; }
-MPCR_D double shfl(unsigned mask, double v, int src) { return __shfl_sync(mask, v, src); }
-MPCR_D int shfl_i(unsigned mask, int v, int src) { return __shfl_sync(mask, v, src); }
-MPCR_D void syncwarp(unsigned mask) { __syncwarp(mask); }
-MPCR_D double shfl_xor(unsigned mask, double v, int m) { return __shfl_xor_sync(mask, v, m); }
-MPCR_D int shfl_xor_i(unsigned mask, int v, int m) { return __shfl_xor_sync(mask, v, m); }
-MPCR_D int atomic_next(int* counter) { return atomicAdd(counter, 1); }
+MPCR_D double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MPCR_D int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MPCR_D void syncwarp() { __syncwarp(); }
+MPCR_D double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+MPCR_D int shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 #endif
 
 #if defined(__CUDACC__)
@@ -73,32 +67,28 @@ MPCR_D double rcp_pivot(double x) {
 #endif
 }
 
-// reductions over the W (32 or 16) lanes of one problem
-template <int W>
-MPCR_NOINLINE double warp_sum(unsigned mask, double v) {
-  for (int m = W / 2; m > 0; m >>= 1) v += shfl_xor(mask, v, m);
+MPCR_NOINLINE double warp_sum(double v) {
+  for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
   return v;
 }
-template <int W>
-MPCR_NOINLINE double warp_max(unsigned mask, double v) {
-  for (int m = W / 2; m > 0; m >>= 1) v = fmax(v, shfl_xor(mask, v, m));
+MPCR_NOINLINE double warp_max(double v) {
+  for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m));
   return v;
 }
-template <int W>
-MPCR_NOINLINE double warp_min(unsigned mask, double v) {
-  for (int m = W / 2; m > 0; m >>= 1) v = fmin(v, shfl_xor(mask, v, m));
+MPCR_NOINLINE double warp_min(double v) {
+  for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m));
   return v;
 }
-template <int W>
-MPCR_D bool warp_all(unsigned mask, bool p) {
+MPCR_D bool warp_all(bool p) {
 #if defined(__CUDA_ARCH__)
-  return __all_sync(mask, p) != 0;      // one VOTE instead of a called butterfly
+  return __all_sync(0xffffffffu, p) != 0;      // one VOTE instead of a called 5-step butterfly
 #else
   int v = p ? 1 : 0;
-  for (int m = W / 2; m > 0; m >>= 1) v &= shfl_xor_i(mask, v, m);
+  for (int m = 16; m > 0; m >>= 1) v &= shfl_xor_i(v, m);
   return v != 0;
 #endif
 }
+MPCR_D bool warp_any(bool p) { return !warp_all(!p); }
 // NaN-propagating max for finiteness checks
 MPCR_D bool finite_d(double v) { return v == v && fabs(v) < 1.0e300; }
 
@@ -113,7 +103,7 @@ constexpr int kOffBase0 = 21;   // derivative part of (thr,thr) (the entry also 
 constexpr int kOffB = 22;       // b = -c_{k+1}  (6)
 constexpr int kOffHs = 28;      // packed sparse stage Hessian (32)
 constexpr int kOffGs = 60;      // dense stage gradient over (z, w) (12)
-constexpr int kOffZero = 109;   // pad slot, kept at 0
+constexpr int kOffZero = 109;   // pad slot, kept at 0 (gs[2] is NOT zero in the restoration phase)
 constexpr int kZeroSlot = kOffZero - 28;   // the always-zero slot relative to kOffHs
 constexpr int kOffK = 72;       // feedback gain (3 x 9); reused for the forward-sweep results
 constexpr int kOffBase1 = 99;   // derivative part of (st,st)
@@ -143,22 +133,19 @@ constexpr int kScrT = 0, kScrG = 9 * kTS, kScrMisc = kScrG + 12 * kGS;   // T an
 template <int IG>
 struct WarpWs {
   static constexpr int kStride = stage_stride(IG);
-  double* base_;   // host build (emulation): start of this problem's workspace; unused on the device
-  int hoff_;       // offset of this problem's workspace inside the block's shared memory (doubles, even):
-                   // 0, or ws_doubles for the upper half-warp's problem
-  int shalf_;      // HALF the offset of the scratch area inside the workspace: written as
+  double* base_;   // host build (emulation): start of the workspace; unused on the device
+  int shalf_;      // HALF the offset of the scratch area inside the shared/host workspace: written as
                    // 2 * shalf_ the compiler sees a 16-byte aligned scratch base (vector LDS/STS)
   MPCR_D double* sm() const {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) double mpcr_dyn_smem[];
-    return mpcr_dyn_smem + hoff_;
+    return mpcr_dyn_smem;
 #else
     return base_;
 #endif
   }
-  MPCR_HD void bind(double* base, int hoff, int N) {
-    base_ = base + hoff;
-    hoff_ = hoff;
+  MPCR_HD void bind(double* base, int N) {
+    base_ = base;
     shalf_ = (N + 1) * (kStride / 2);
   }
   MPCR_D double* T() const { return sm() + 2 * shalf_ + kScrT; }       // [9][kTS]
@@ -270,12 +257,7 @@ struct ProblemView {     // uniform over the warp
 static_assert(sizeof(Params) <= kPrmSlots * sizeof(double), "kPrmSlots too small");
 static_assert(sizeof(ProblemView) <= kPbSlots * sizeof(double), "kPbSlots too small");
 constexpr int kScratch = kScrMisc + kMisc + kPrmSlots + kPbSlots;
-// workspace of ONE problem (a HALF kernel keeps two per warp)
 MPCR_HD int ws_doubles(int N, int ig = 0) { return (N + 1) * stage_stride(ig) + kScratch; }
-
-MPCR_HD int lam_g_stride(const Config& c) {
-  return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
-}
 
 struct SolveOut {        // pointers already offset to this problem
   double* U; double* X; double* S; double* eC; double* eL; double* lam_g;
@@ -285,9 +267,7 @@ struct SolveOut {        // pointers already offset to this problem
 // solver phases: every heavy routine has exactly ONE call site inside the phase loop
 // (keeps the kernel's instruction footprint inside the SM instruction cache)
 enum Phase : int { kPhInit = 0, kPhInit2 = 1, kPhNewton = 2, kPhBacktrack = 3, kPhSoc = 4,
-                   kPhRestoCheck = 5,     // restoration: evaluate the ORIGINAL merit at the new point
-                   kPhLoad = 6,           // fetch the next problem of the batch and set it up
-                   kPhExit = 7 };         // the batch has run dry
+                   kPhRestoCheck = 5 };   // restoration: evaluate the ORIGINAL merit at the new point
 
 // ---------------------------------------------------------------------------
 // The solver.  All members are per-lane unless noted "uniform".
@@ -303,40 +283,23 @@ struct RowState {
   // of the proximity term over the same 9 variables
   double xr[9], pg[9];
   double osave[12];         // the outer problem's scalars while the restoration phase runs
-  // line-search scratch: second-order-correction right-hand side, the plain step saved while a
-  // correction is tried, d_r - s_r at the trial point
-  double d_soc[kNumRows], sv_dsr[kNumRows], tp_rd[kNumRows];
 };
 
 // RESTO: compile the feasibility-restoration phase in (mpcr_config.restoration); the RESTO = false
 //        instantiation is the plain solver without any of its code or registers.
 // IG:    integrator of the dynamics rows, 0 = explicit Euler (reference), 1 = RK4 (32-entry stage
 //        linearisation).
-// HALF:  two problems per warp (horizons up to 16): lanes 0-15 and 16-31 are two independent
-//        lock-step groups with their own problem stream, workspace and participation mask.
-template <int MODEL, bool RESTO = false, int IG = 0, bool HALF = false>
+template <int MODEL, bool RESTO = false, int IG = 0>
 struct WarpSolver {
-  static constexpr int W = HALF ? 16 : 32;          // lanes per problem
-  static constexpr int kStride = stage_stride(IG);
   const Config& cfg;
   const IpmOptions& o;
   WarpWs<IG> ws;
-  // per-problem parameters and inputs (uniform over the problem's lanes): ONE copy in shared memory,
-  // written by load_problem, instead of one per-lane copy in local memory behind L2 latency
+  // per-problem parameters and inputs (uniform over the warp): ONE copy in shared memory, written
+  // by solve_problem, instead of 32 per-lane copies in local memory behind L2 latency
   MPCR_D const Params& prm() const { return *reinterpret_cast<const Params*>(ws.prm_mem()); }
   MPCR_D const ProblemView& pbv() const { return *reinterpret_cast<const ProblemView*>(ws.pb_mem()); }
-  int lane, N;              // lane = stage index inside this problem (0..W-1)
-  int lbase;                // first hardware lane of this problem's group (0, or 16 for the upper half)
-  unsigned mask;            // participation mask of this problem's lanes
+  int lane, N;
   bool act;
-  // collectives of this problem's lane group
-  MPCR_D double shf(double v, int src) const { return shfl(mask, v, lbase + src); }
-  MPCR_D int shf_i(int v, int src) const { return shfl_i(mask, v, lbase + src); }
-  MPCR_D void sync() const { syncwarp(mask); }
-  MPCR_D double wsum(double v) const { return warp_sum<W>(mask, v); }
-  MPCR_D double wmax(double v) const { return warp_max<W>(mask, v); }
-  MPCR_D double wmin(double v) const { return warp_min<W>(mask, v); }
-  MPCR_D bool wall(bool p) const { return warp_all<W>(mask, p); }
   // primal iterate
   double x[6], sh, u[2];
   // multipliers (dynamics rows carry lam = dc * y_scaled; y0 uniform: x0 rows (6) + s0 row)
@@ -355,7 +318,7 @@ struct WarpSolver {
   // filter: one entry per lane
   double filt_th, filt_ph;
   int filt_n;
-  // feasibility restoration (quadratic-penalty variant): while `in_resto()` is set
+  // feasibility restoration (quadratic-penalty variant, same text as LaneSolver): while `in_resto()` is set
   // the objective is wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 and the rows' multipliers are o.resto_weight (d - s)
   bool resto_;
   MPCR_D bool in_resto() const { return RESTO && resto_; }
@@ -365,15 +328,12 @@ struct WarpSolver {
   unsigned colslot_hi;
   double dwflag;            // 1 if diagonal entry (lane, lane) receives delta_w
 
-  MPCR_D WarpSolver(const Config& c, RowState& rows, double* wsbase, const BatchOut& bout, int trows)
-      : cfg(c), o(c.o), R(rows), bo(bout), trace_rows(trows) {
-    const int hw = lane_id();
-    lane = hw & (W - 1);
-    lbase = hw & ~(W - 1);
-    mask = HALF ? (0xffffu << lbase) : kFullMask;
+  MPCR_D WarpSolver(const Config& c, RowState& rows, double* wsbase)
+      : cfg(c), o(c.o), R(rows) {
+    lane = lane_id();
     N = c.N;
     act = lane < N;
-    ws.bind(wsbase, lbase ? ws_doubles(N, IG) : 0, N);
+    ws.bind(wsbase, N);
     colslot_lo = 0ull;
     colslot_hi = 0u;
     for (int r = 0; r < 12; ++r) {
@@ -440,13 +400,13 @@ struct WarpSolver {
                           double& shp, double* up) const {
     int src = prev_lane();
     for (int k = 0; k < 6; ++k) {
-      double t = shf(xx[k], src);
+      double t = shfl(xx[k], src);
       xp[k] = (lane == 0) ? pbv().x0[k] : t;
     }
-    double t = shf(shh, src);
+    double t = shfl(shh, src);
     shp = (lane == 0) ? pbv().s0 : t;
-    up[0] = shf(uu[0], src);   // lane 0 receives u_{N-1} (wrap rows)
-    up[1] = shf(uu[1], src);
+    up[0] = shfl(uu[0], src);   // lane 0 receives u_{N-1} (wrap rows)
+    up[1] = shfl(uu[1], src);
   }
 
   // -------------------------------------------------------------------------
@@ -524,60 +484,38 @@ struct WarpSolver {
     }
     double bar = act ? (-log_d(prod) + o.kappa_d * lin) : 0.0;
     fin = fin && finite_d(fl) && finite_d(th) && finite_d(bar);
-    t.finite = wall(fin);
-    t.f = dfu * wsum(fl);
-    t.theta = wsum(th);
-    t.barB = wsum(bar);
+    t.finite = warp_all(fin);
+    t.f = dfu * warp_sum(fl);
+    t.theta = warp_sum(th);
+    t.barB = warp_sum(bar);
   }
 
   // -------------------------------------------------------------------------
   // Derivative evaluation at the current iterate; fills the stage storage.
   // mode 0: Newton step (exact Hessian), mode 1: least-squares multiplier init
   // -------------------------------------------------------------------------
-  double gcost[5];        // df * grad cost of state lane+1 over (X, Y, s, vx, vy) (incl -lambda_s)
-  double gC[3];           // ddl * grad e_C over (X, Y, s) at state lane+1 (lane row)
-  double sigc_prev;       // sigma_k - sigma_{k-1} (0 for lane 0)
-  double hcp6[6];         // df * cost Hessian over (X, Y, s) of state `lane` (+ lane-row curvature)
+  StageLin lin;           // Jacobian blocks of stage `lane`
+  double linx[IG ? 11 : 1];   // RK4: the 11 extra entries of the stage Jacobian (kOffAx)
 
   // x+ of the NLP's dynamics rows: explicit Euler (reference) or RK4 of the same vector field
   MPCR_D void model_step(const double* xp, const double* uu, double* f) const {
     if (IG) rk4_model(MODEL, xp, uu, cfg.Ts, nullptr, f, nullptr, nullptr);
     else f_model(MODEL, xp, uu, cfg.Ts, f);
   }
-
-  // Jacobian of the stage map in the solver's layout: A[0..20] = StageLin, Ax[0..10] = RK4 extras
-  MPCR_D void stage_lin(const double* xp, const double* uu, const double* lz, double* A, double* Ax,
-                        double* hm) const {
-    if (!IG) {
-      StageLin lin;
-      lin_model(MODEL, xp, uu, cfg.Ts, lz, nullptr, lin, hm);
-      for (int k = 0; k < 3; ++k) { A[k] = lin.aX[k]; A[3 + k] = lin.aY[k]; }
-      for (int i = 0; i < 3; ++i)
-        for (int k = 0; k < 3; ++k) A[6 + 3 * i + k] = lin.d[i][k];
-      for (int i = 0; i < 3; ++i)
-        for (int k = 0; k < 2; ++k) A[15 + 2 * i + k] = lin.bu[i][k];
-    } else {
-      double f[6], J[6][6];
-      rk4_model(MODEL, xp, uu, cfg.Ts, lz, f, J, hm);
-      for (int a = 0; a < 3; ++a) { A[a] = J[0][a]; A[3 + a] = J[1][a]; Ax[a] = J[0][3 + a]; Ax[3 + a] = J[1][3 + a]; }
-      for (int i = 0; i < 3; ++i) {
-        for (int a = 0; a < 3; ++a) A[6 + 3 * i + a] = J[3 + i][1 + a];
-        for (int a = 0; a < 2; ++a) A[15 + 2 * i + a] = J[3 + i][4 + a];
-      }
-      Ax[6] = J[2][1];
-      Ax[7] = J[2][2];
-      Ax[8] = J[2][4];
-      Ax[9] = J[2][5];
-      Ax[10] = J[2][3];
-    }
-  }
-  // this lane's stage Jacobian back from the stage record (written by eval_derivs)
-  MPCR_D void load_lin(double* A, double* Ax) const {
-    const double* st = ws.st(act ? lane : 0);
-    for (int c = 0; c < kLinEuler; ++c) A[c] = st[kOffA + c];
+  // this lane's stage Jacobian in the solver's layout: A[0..20] = StageLin, Ax[0..10] = RK4 extras
+  MPCR_D void lin_arrays(double* A, double* Ax) const {
+    for (int k = 0; k < 3; ++k) { A[k] = lin.aX[k]; A[3 + k] = lin.aY[k]; }
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) A[6 + 3 * i + k] = lin.d[i][k];
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 2; ++k) A[15 + 2 * i + k] = lin.bu[i][k];
     if (IG)
-      for (int c = 0; c < 11; ++c) Ax[c] = st[kOffAx + c];
+      for (int k = 0; k < 11; ++k) Ax[k] = linx[k];
   }
+  double gcost[5];        // df * grad cost of state lane+1 over (X, Y, s, vx, vy) (incl -lambda_s)
+  double gC[3];           // ddl * grad e_C over (X, Y, s) at state lane+1 (lane row)
+  double sigc_prev;       // sigma_k - sigma_{k-1} (0 for lane 0)
+  double hcp6[6];         // df * cost Hessian over (X, Y, s) of state `lane` (+ lane-row curvature)
 
   MPCR_D void eval_derivs(int mode) {
     double xp[6], shp, up[2];
@@ -585,8 +523,22 @@ struct WarpSolver {
     double hm[kHmDoubles];
     double lz[6];
     for (int k = 0; k < 6; ++k) lz[k] = (mode == 0) ? lam[k] : 0.0;
-    double A[kLinEuler], Ax[12];
-    stage_lin(xp, u, lz, A, Ax, hm);
+    if (!IG) {
+      lin_model(MODEL, xp, u, cfg.Ts, lz, nullptr, lin, hm);
+    } else {
+      double f[6], J[6][6];
+      rk4_model(MODEL, xp, u, cfg.Ts, lz, f, J, hm);
+      for (int a = 0; a < 3; ++a) { lin.aX[a] = J[0][a]; lin.aY[a] = J[1][a]; linx[a] = J[0][3 + a]; linx[3 + a] = J[1][3 + a]; }
+      for (int i = 0; i < 3; ++i) {
+        for (int a = 0; a < 3; ++a) lin.d[i][a] = J[3 + i][1 + a];
+        for (int a = 0; a < 2; ++a) lin.bu[i][a] = J[3 + i][4 + a];
+      }
+      linx[6] = J[2][1];
+      linx[7] = J[2][2];
+      linx[8] = J[2][4];
+      linx[9] = J[2][5];
+      linx[10] = J[2][3];
+    }
     StageCost sc;
     stage_cost(prm(), pbv().cx, pbv().cy, x, sh, 2, sc);
     gcost[0] = df * sc.g3[0];
@@ -634,21 +586,25 @@ struct WarpSolver {
     }
     double hcp[8];
     for (int k = 0; k < 8; ++k) {
-      double t = shf(hc[k], prev_lane());
+      double t = shfl(hc[k], prev_lane());
       hcp[k] = (lane == 0) ? 0.0 : t;
     }
     double hyrp[2] = {0.0, 0.0};
     if (in_resto()) {
       for (int k = 0; k < 2; ++k) {
-        double t = shf(hyr[k], prev_lane());
+        double t = shfl(hyr[k], prev_lane());
         hyrp[k] = (lane == 0) ? 0.0 : t;
       }
     }
     if (act) {
       double* st = ws.st(lane);
-      for (int k = 0; k < kLinEuler; ++k) st[kOffA + k] = A[k];
+      for (int k = 0; k < 3; ++k) { st[kOffA + k] = lin.aX[k]; st[kOffA + 3 + k] = lin.aY[k]; }
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k) st[kOffA + 6 + 3 * i + k] = lin.d[i][k];
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 2; ++k) st[kOffA + 15 + 2 * i + k] = lin.bu[i][k];
       if (IG)
-        for (int k = 0; k < 11; ++k) st[kOffAx + k] = Ax[k];
+        for (int k = 0; k < 11; ++k) st[kOffAx + k] = linx[k];
       double* hs = st + kOffHs;
       // (thr,thr), (st,st) also receive row terms: their derivative part is kept in `base`;
       // the (X,Y,s) block's derivative part stays in registers (hcp6)
@@ -770,27 +726,27 @@ struct WarpSolver {
       }
     }
     const bool wrap0 = (lane == 0);   // rows kDThr/kDSt of lane 0 are the non-local wrap rows
-    double Dw0 = shf(Dthr, 0), Dw1 = shf(Dst, 0);
-    double ew0 = shf(ethr, 0), ew1 = shf(esr, 0);
+    double Dw0 = shfl(Dthr, 0), Dw1 = shfl(Dst, 0);
+    double ew0 = shfl(ethr, 0), ew1 = shfl(esr, 0);
     Dw[0] = Dw0;
     Dw[1] = Dw1;
     // cost gradient / lane-row data of state `lane` live in the previous lane
     double gcp[5], gCp[3];
     for (int k = 0; k < 5; ++k) {
-      double t = shf(gcost[k], prev_lane());
+      double t = shfl(gcost[k], prev_lane());
       gcp[k] = (lane == 0) ? 0.0 : t;
     }
-    double elane_p = shf(elane, prev_lane()), Dlane_p = shf(Dlane, prev_lane());
+    double elane_p = shfl(elane, prev_lane()), Dlane_p = shfl(Dlane, prev_lane());
     if (lane == 0) { elane_p = 0.0; Dlane_p = 0.0; }
     for (int k = 0; k < 3; ++k) {
-      double t = shf(gC[k], prev_lane());
+      double t = shfl(gC[k], prev_lane());
       gCp[k] = (lane == 0) ? 0.0 : t;
     }
     // restoration: proximity gradient over (yaw, r) of state `lane` (previous lane) and over this
     // stage's inputs
     double pgy = 0.0, pgr = 0.0, pgt = 0.0, pgs = 0.0;
     if (in_resto()) {
-      const double t0 = shf(R.pg[2], prev_lane()), t1 = shf(R.pg[5], prev_lane());
+      const double t0 = shfl(R.pg[2], prev_lane()), t1 = shfl(R.pg[5], prev_lane());
       pgy = (lane == 0) ? 0.0 : t0;
       pgr = (lane == 0) ? 0.0 : t1;
       pgt = R.pg[7];
@@ -895,18 +851,21 @@ struct WarpSolver {
     {
       const double* stN = ws.st(N);
       double* P0 = G;       // staging of the terminal matrix, stride kPS (G is free until round 2)
-      for (int e = lane; e < 81; e += W) {
-        int r = e / 9, c = e % 9;
-        P0[r * kPS + c] = stage_entry(stN, slot_of(r, c), dw);
+      for (int j = 0; j < 3; ++j) {
+        int e = lane + 32 * j;
+        if (e < 81) {
+          int r = e / 9, c = e % 9;
+          P0[r * kPS + c] = stage_entry(stN, slot_of(r, c), dw);
+        }
       }
-      sync();
+      syncwarp();
       const int c = lane < 9 ? lane : 0;
       for (int a = 0; a < 9; ++a) pr[a] = P0[a * kPS + c];
       pj[0] = stN[kOffGs + c];
       pj[1] = 0.0;
       pj[2] = 0.0;
     }
-    sync();
+    syncwarp();
     bool ok = true;
     ric_nneg = 0;
     const double dwc = dwflag * dw;
@@ -927,7 +886,7 @@ struct WarpSolver {
         T[lane * kTS + 13] = pj[1];
         T[lane * kTS + 14] = pj[2];
       }
-      sync();
+      syncwarp();
       // ---- round 2: column `lane` of G = M' T + (stage Hessian | gradient | wrap vector) -----
       if (lane < 12 + nrhs) {
         double tc[9], A[kLinEuler], Ax[12], out[12];
@@ -948,7 +907,7 @@ struct WarpSolver {
           G[(9 + (lane - 13)) * kGS + lane] += a;
         }
       }
-      sync();
+      syncwarp();
       // ---- round 3: LDL' of H_ww (every lane), gains, cost-to-go update in registers -------
       const double h00 = G[9 * kGS + 9], h10 = G[10 * kGS + 9], h20 = G[11 * kGS + 9];
       const double h11 = G[10 * kGS + 10], h21 = G[11 * kGS + 10], h22 = G[11 * kGS + 11];
@@ -1012,12 +971,11 @@ struct WarpSolver {
       // readers (round 2) are behind the barrier above
     }
     if (!ok) return false;
-    sync();
-    // ---- forward sweep: three lane groups (W / 3 lanes each) each roll out ONE right-hand side;
+    syncwarp();
+    // ---- forward sweep: lane groups 0-10 / 11-21 / 22-31 each roll out ONE right-hand side;
     //      the group leaders park (z_{k+1}, w_k) in stage k's (now dead) gain slot -----------
-    constexpr int kGrp = W / 3;    // lanes per right-hand side (the last group takes the remainder)
-    const int grp = (nrhs == 1) ? 0 : (lane < kGrp ? 0 : (lane < 2 * kGrp ? 1 : 2));
-    const bool leader = (nrhs == 1) ? (lane == 0) : (lane == 0 || lane == kGrp || lane == 2 * kGrp);
+    const int grp = (nrhs == 1) ? 0 : (lane < 11 ? 0 : (lane < 22 ? 1 : 2));
+    const bool leader = (nrhs == 1) ? (lane == 0) : (lane == 0 || lane == 11 || lane == 22);
     const double bsel = (grp == 0) ? 1.0 : 0.0;
     double z[9];
     for (int a = 0; a < 9; ++a) z[a] = 0.0;
@@ -1038,7 +996,7 @@ struct WarpSolver {
       applyMx<IG>(z, w, A, Ax, Ts, zn);
       for (int a = 0; a < 6; ++a) zn[a] += bsel * st[kOffB + a];
       for (int a = 0; a < 9; ++a) z[a] = zn[a];
-      sync();                       // every lane has read K_k before it is overwritten
+      syncwarp();                       // every lane has read K_k before it is overwritten
       if (leader) {
         double* dst = st + kOffK + grp * 9;
         for (int a = 0; a < 7; ++a) dst[a] = zn[a];
@@ -1046,7 +1004,7 @@ struct WarpSolver {
         dst[8] = w[1];
       }
     }
-    sync();
+    syncwarp();
     return true;      // stage k's gain slot now holds (dz_{k+1} (7), dw_k (2)) of the 3 right-hand sides
   }
 
@@ -1080,9 +1038,9 @@ struct WarpSolver {
     if (cfg.wrap) {
       double t0[2], Mm[2][2];
       for (int i = 0; i < 2; ++i) {
-        t0[i] = shf(mw[0][i], 0) - shf(mw[0][i], N - 1);
+        t0[i] = shfl(mw[0][i], 0) - shfl(mw[0][i], N - 1);
         for (int kk = 0; kk < 2; ++kk)
-          Mm[i][kk] = shf(mw[1 + kk][i], 0) - shf(mw[1 + kk][i], N - 1);
+          Mm[i][kk] = shfl(mw[1 + kk][i], 0) - shfl(mw[1 + kk][i], N - 1);
       }
       const double a00 = 1.0 - Mm[0][0] * Dw[0], a01 = -Mm[0][1] * Dw[1];
       const double a10 = -Mm[1][0] * Dw[0], a11 = 1.0 - Mm[1][1] * Dw[1];
@@ -1104,11 +1062,11 @@ struct WarpSolver {
     // costates: pi_j = local_j + A_j' pi_{j+1}, local_j = Q_j dz_j + S_j' dw_j + q_j
     double dzp[7];
     for (int a = 0; a < 6; ++a) {
-      double t = shf(dx[a], prev_lane());
+      double t = shfl(dx[a], prev_lane());
       dzp[a] = (lane == 0) ? 0.0 : t;
     }
     {
-      double t = shf(dsh, prev_lane());
+      double t = shfl(dsh, prev_lane());
       dzp[6] = (lane == 0) ? 0.0 : t;
     }
     double* loc = ws.T();   // scratch [(N+1)][7]: T (162) + G (192) are contiguous
@@ -1140,7 +1098,7 @@ struct WarpSolver {
         }
       }
     }
-    sync();
+    syncwarp();
     double pi[7];
     for (int a = 0; a < 7; ++a) pi[a] = loc[N * 7 + a];
     for (int a = 0; a < 6; ++a) newlam[a] = 0.0;
@@ -1169,7 +1127,7 @@ struct WarpSolver {
         for (int a = 0; a < 6; ++a) newlam[a] = -pi[a];
     }
     for (int a = 0; a < 7; ++a) newy0[a] = -pi[a];
-    sync();
+    syncwarp();
     return true;
   }
 
@@ -1192,7 +1150,7 @@ struct WarpSolver {
   MPCR_D Errors compute_errors() const {
     // t = A' lam: contributions of this stage's dynamics rows to (x_k, u_k)
     double A[kLinEuler], Ax[12], lv[9], out[12];
-    load_lin(A, Ax);
+    lin_arrays(A, Ax);
     for (int k = 0; k < 6; ++k) lv[k] = act ? lam[k] : 0.0;
     lv[6] = lv[7] = lv[8] = 0.0;
     mulMx<IG>(lv, A, Ax, cfg.Ts, out);
@@ -1200,17 +1158,17 @@ struct WarpSolver {
     double dinf = 0.0;
     double txn[6];
     for (int a = 0; a < 6; ++a) {
-      double t = shf(out[a], next_lane());
+      double t = shfl(out[a], next_lane());
       txn[a] = last ? 0.0 : t;
     }
     const double ydl = on(kLane) ? R.yd[kLane] : 0.0;
     const double gx[6] = {gcost[0] + ydl * gC[0], gcost[1] + ydl * gC[1], in_resto() ? R.pg[2] : 0.0, gcost[3],
                           gcost[4], in_resto() ? R.pg[5] : 0.0};
-    const double yprog_n_raw = shf(R.yd[kProg], next_lane());
+    const double yprog_n_raw = shfl(R.yd[kProg], next_lane());
     const double yprog_n = last ? 0.0 : yprog_n_raw;
-    const double ydthr_n = shf(on(kDThr) ? R.yd[kDThr] : 0.0, next_lane());
-    const double ydst_n = shf(on(kDSt) ? R.yd[kDSt] : 0.0, next_lane());
-    const double sig_n_raw = shf(sigc_prev, next_lane());
+    const double ydthr_n = shfl(on(kDThr) ? R.yd[kDThr] : 0.0, next_lane());
+    const double ydst_n = shfl(on(kDSt) ? R.yd[kDSt] : 0.0, next_lane());
+    const double sig_n_raw = shfl(sigc_prev, next_lane());
     const double sig_n = last ? 0.0 : sig_n_raw;
     double prinf = 0.0, pmax = -1.0e300, pmin = 1.0e300, sum_y = 0.0, sum_v = 0.0;
     double vio = 0.0;      // violation of the ORIGINAL constraints (unscaled, unrelaxed bounds)
@@ -1267,13 +1225,13 @@ struct WarpSolver {
       if (row_hasU(r)) vio = fmax(vio, val - bh);
     }
     Errors e;
-    e.dual_inf = wmax(dinf);
-    e.pr_inf = wmax(prinf);
-    e.viol = wmax(vio);
-    e.prod_max = wmax(pmax);
-    e.prod_min = wmin(pmin);
-    sum_y = wsum(sum_y);
-    sum_v = wsum(sum_v);
+    e.dual_inf = warp_max(dinf);
+    e.pr_inf = warp_max(prinf);
+    e.viol = warp_max(vio);
+    e.prod_max = warp_max(pmax);
+    e.prod_min = warp_min(pmin);
+    sum_y = warp_sum(sum_y);
+    sum_v = warp_sum(sum_v);
     const double smax = o.s_max;
     // s_d = max(s_max, mean multiplier) / s_max (Waechter & Biegler eq. (6)), kept as reciprocals
     // (exactly 1 while the mean stays below s_max)
@@ -1287,12 +1245,12 @@ struct WarpSolver {
   // filter --------------------------------------------------------------------
   MPCR_D bool filter_ok(double th, double ph) const { return filter_ok_in(th, ph, filt_th, filt_ph, filt_n); }
   MPCR_D bool filter_ok_in(double th, double ph, double fth, double fph, int fn) const {
-    int n = fn < W ? fn : W;
+    int n = fn < 32 ? fn : 32;
     bool ok = (lane >= n) || (th <= fth) || (ph <= fph);
-    return wall(ok);
+    return warp_all(ok);
   }
   MPCR_D void filter_add(double th, double ph) {
-    if (lane == (filt_n & (W - 1))) { filt_th = th; filt_ph = ph; }
+    if (lane == (filt_n & 31)) { filt_th = th; filt_ph = ph; }
     filt_n++;
   }
   MPCR_D static bool cmp_le(double a, double b, double ref) {
@@ -1303,9 +1261,9 @@ struct WarpSolver {
   // pass accumulates this lane's share of grad_s(phi)' ds and of theta = |c|_1 + |d - s|_1
   MPCR_D double slack_steps(const double* rdv, double dwu, double& gs_ds, double& th_loc) {
     double dup[2], dshp;
-    dup[0] = shf(du[0], prev_lane());
-    dup[1] = shf(du[1], prev_lane());
-    double t = shf(dsh, prev_lane());
+    dup[0] = shfl(du[0], prev_lane());
+    dup[1] = shfl(du[1], prev_lane());
+    double t = shfl(dsh, prev_lane());
     dshp = (lane == 0) ? 0.0 : t;
     double a = 1.0, g = 0.0, th = 0.0;
     if (act)
@@ -1347,34 +1305,11 @@ struct WarpSolver {
     }
     gs_ds = g;
     th_loc = th;
-    return wmin(a);
+    return warp_min(a);
   }
 
   // -------------------------------------------------------------------------
-  // ---- phase-loop state (one problem stream per lane group) -----------------------------------
-  int pb;                   // index of the current problem in the batch
-  const BatchOut& bo;       // output arrays of the batch (kernel parameters)
-  int trace_rows;
-  int phase, status, it, acc_count, n_ls, soc_count, ls_fail_mode;
-  bool cur_finite, soc_done, f_type;
-  double theta_max, theta_min, mu_floor;
-  double dw, dw_last, last_alpha, last_dw;
-  double alpha, a_soc, amin, gpd, theta, phi, th_old;
-  double c_soc[6];
-  // plain (non-SOC) step saved while a second-order correction is being tried
-  double sv_dx[6], sv_dsh, sv_du[2], sv_lam[6], sv_y0[7];
-  Point tp;
-  // restoration bookkeeping (the outer problem's scalars are parked in R.osave)
-  bool want_resto, reinit;
-  int resto_it;
-  // polish (mpcr_config.polish_tol > 0): after the first termination the iteration continues to the
-  // tighter tolerance; status / iters of the first termination are what is reported
-  double tol_cur;
-  bool polishing;
-  int first_status, first_iters;
-
-  // Initial state of the solver for the problem whose inputs load_problem() put into shared memory.
-  MPCR_D void setup() {
+  MPCR_D void solve(const SolveOut& out) {
     const double inf = 1.0e300;
     // ---- rows ---------------------------------------------------------------
     rowmask = 0;
@@ -1401,7 +1336,7 @@ struct WarpSolver {
       for (int k = 0; k < 6; ++k) { xr[k] = pbv().x0[k]; x[k] = pbv().x0[k]; }
 #pragma unroll 1
       for (int k = 0; k < N; ++k) {
-        double uk[2] = {shf(u[0], k), shf(u[1], k)};
+        double uk[2] = {shfl(u[0], k), shfl(u[1], k)};
         double fn[6];
         if (IG) rk4_model(kDynamic, xr, uk, cfg.Ts, nullptr, fn, nullptr, nullptr);
         else f_dynamic(xr, uk, cfg.Ts, fn);            // always f_vehicle (MPC.py:129)
@@ -1436,39 +1371,40 @@ struct WarpSolver {
 #pragma unroll 1
       for (int r = 0; r < kNumRows; ++r)
         if (on(r)) { nr += 1; nb += (row_hasL(r) ? 1 : 0) + (row_hasU(r) ? 1 : 0); }
-      n_eq_ineq = (int)(wsum((double)nr) + 0.5) + 6 * N + 7;
-      n_bounds = (int)(wsum((double)nb) + 0.5);
+      n_eq_ineq = (int)(warp_sum((double)nr) + 0.5) + 6 * N + 7;
+      n_bounds = (int)(warp_sum((double)nb) + 0.5);
     }
     // provisional (unscaled, unrelaxed) bounds so that lo()/hi() are defined early
     if (lane < kNumRows) { ws.misc()[lane] = -inf; ws.misc()[kNumRows + lane] = inf; }
-    sync();
+    syncwarp();
 
-    phase = kPhInit;
-    status = kMaxIterExceeded;
-    it = 0; acc_count = 0; n_ls = 0; soc_count = 0; ls_fail_mode = 0;
-    cur_finite = true; soc_done = false; f_type = false;
-    theta_max = 0.0; theta_min = 0.0; mu_floor = 0.0;
-    dw = 0.0; dw_last = 0.0; last_alpha = 0.0; last_dw = 0.0;
-    alpha = 0.0; a_soc = 0.0; amin = 0.0; gpd = 0.0; theta = 0.0; phi = 0.0; th_old = 0.0;
-    sv_dsh = 0.0; sv_du[0] = sv_du[1] = 0.0;
+    // ---- phase-loop state ------------------------------------------------------------
+    int phase = kPhInit;
+    int status = kMaxIterExceeded;
+    int it = 0, acc_count = 0, n_ls = 0, soc_count = 0, ls_fail_mode = 0;
+    bool cur_finite = true, soc_done = false, f_type = false;
+    double theta_max = 0.0, theta_min = 0.0, mu_floor = 0.0;
+    double dw = 0.0, dw_last = 0.0, last_alpha = 0.0, last_dw = 0.0;
+    double alpha = 0.0, a_soc = 0.0, amin = 0.0, gpd = 0.0, theta = 0.0, phi = 0.0, th_old = 0.0;
+    double c_soc[6], d_soc[kNumRows];
+    // plain (non-SOC) step saved while a second-order correction is being tried
+    double sv_dx[6], sv_dsh = 0.0, sv_du[2] = {0.0, 0.0}, sv_dsr[kNumRows], sv_lam[6], sv_y0[7];
 #pragma unroll 1
-    for (int r = 0; r < kNumRows; ++r) { R.d_soc[r] = 0.0; R.sv_dsr[r] = 0.0; R.tp_rd[r] = 0.0; }
+    for (int r = 0; r < kNumRows; ++r) { d_soc[r] = 0.0; sv_dsr[r] = 0.0; }
     for (int a = 0; a < 6; ++a) { c_soc[a] = 0.0; sv_dx[a] = 0.0; sv_lam[a] = 0.0; }
     for (int a = 0; a < 7; ++a) sv_y0[a] = 0.0;
-    want_resto = false; reinit = false;
-    resto_it = 0;
-    tol_cur = o.tol;
-    polishing = false;
-    first_status = 0; first_iters = 0;
-  }
+    Point tp;
+    double tp_rd[kNumRows];
+    // restoration bookkeeping (the outer problem's scalars are parked in R.osave)
+    bool want_resto = false, reinit = false;
+    int resto_it = 0;
+    // polish (mpcr_config.polish_tol > 0): after the first termination the iteration continues to the
+    // tighter tolerance; status / iters of the first termination are what is reported
+    double tol_cur = o.tol;
+    bool polishing = false;
+    int first_status = 0, first_iters = 0;
 
-  // One pass of the phase loop.  Returns true when the problem has terminated (`status` is final).
-  MPCR_D bool iterate() {
-    const double inf = 1.0e300;
-    double* const d_soc = R.d_soc;
-    double* const sv_dsr = R.sv_dsr;
-    double* const tp_rd = R.tp_rd;
-    {
+    while (true) {
       if (RESTO && want_resto) {
         // ---- enter the restoration phase at the current iterate (x_R, s_R) ---------------------
         want_resto = false;
@@ -1513,7 +1449,7 @@ struct WarpSolver {
           R.vU[r] = row_hasU(r) ? o.bound_mult_init_val : 0.0;
         }
         for (int a = 0; a < 7; ++a) y0[a] = 0.0;
-        mu = fmax(mu, wmax(vmax));
+        mu = fmax(mu, warp_max(vmax));
         tau = fmax(o.tau_min, 1.0 - mu);
         R.osave[10] = sqrt(mu);
         df = 1.0;
@@ -1532,34 +1468,30 @@ struct WarpSolver {
           // multiplier re-initialisation after restoration: scaling, bounds and mu stay as they are
         } else if (phase == kPhInit) {
           // ---- gradient-based scaling at the starting point ----------------------------
-          double sig_n_raw = shf(sigc_prev, next_lane());
+          double sig_n_raw = shfl(sigc_prev, next_lane());
           double sig_n = (lane == N - 1) ? 0.0 : sig_n_raw;
           double g = 0.0;
           if (act) {
             for (int k = 0; k < 5; ++k) g = fmax(g, fabs(gcost[k]));
             g = fmax(g, fabs(2.0 * prm().beta_delta * (sigc_prev - sig_n)));
           }
-          g = wmax(g);
+          g = warp_max(g);
           if (g > o.nlp_scaling_max_gradient)
             df = fmax(o.nlp_scaling_max_gradient / g, o.nlp_scaling_min_value);
           double rm[6];
-          {
-            double A[kLinEuler], Ax[12];
-            load_lin(A, Ax);
-            rm[0] = fmax(1.0, fmax(fabs(A[0]), fmax(fabs(A[1]), fabs(A[2]))));
-            rm[1] = fmax(1.0, fmax(fabs(A[3]), fmax(fabs(A[4]), fabs(A[5]))));
-            rm[2] = fmax(1.0, fabs(cfg.Ts));
-            if (IG) {
-              for (int a = 0; a < 3; ++a) { rm[0] = fmax(rm[0], fabs(Ax[a])); rm[1] = fmax(rm[1], fabs(Ax[3 + a])); }
-              rm[2] = fmax(1.0, fabs(Ax[10]));
-              for (int a = 0; a < 4; ++a) rm[2] = fmax(rm[2], fabs(Ax[6 + a]));
-            }
-            for (int i = 0; i < 3; ++i) {
-              double m = 1.0;
-              for (int k = 0; k < 3; ++k) m = fmax(m, fabs(A[6 + 3 * i + k]));
-              for (int k = 0; k < 2; ++k) m = fmax(m, fabs(A[15 + 2 * i + k]));
-              rm[3 + i] = m;
-            }
+          rm[0] = fmax(1.0, fmax(fabs(lin.aX[0]), fmax(fabs(lin.aX[1]), fabs(lin.aX[2]))));
+          rm[1] = fmax(1.0, fmax(fabs(lin.aY[0]), fmax(fabs(lin.aY[1]), fabs(lin.aY[2]))));
+          rm[2] = fmax(1.0, fabs(cfg.Ts));
+          if (IG) {
+            for (int a = 0; a < 3; ++a) { rm[0] = fmax(rm[0], fabs(linx[a])); rm[1] = fmax(rm[1], fabs(linx[3 + a])); }
+            rm[2] = fmax(1.0, fabs(linx[10]));
+            for (int a = 0; a < 4; ++a) rm[2] = fmax(rm[2], fabs(linx[6 + a]));
+          }
+          for (int i = 0; i < 3; ++i) {
+            double m = 1.0;
+            for (int k = 0; k < 3; ++k) m = fmax(m, fabs(lin.d[i][k]));
+            for (int k = 0; k < 2; ++k) m = fmax(m, fabs(lin.bu[i][k]));
+            rm[3 + i] = m;
           }
           for (int k = 0; k < 6; ++k)
             dcs[k] = (rm[k] > o.nlp_scaling_max_gradient)
@@ -1568,7 +1500,7 @@ struct WarpSolver {
           if (cfg.lane_con && gl > o.nlp_scaling_max_gradient)
             ddl = fmax(o.nlp_scaling_max_gradient / gl, o.nlp_scaling_min_value);
           // the lane-row scale is made uniform over the warp (its bounds live in shared memory)
-          ddl = wmin(act ? ddl : 1.0);
+          ddl = warp_min(act ? ddl : 1.0);
           for (int k = 0; k < 5; ++k) gcost[k] *= df;    // eval_derivs ran with df = ddl = 1
           for (int k = 0; k < 3; ++k) gC[k] *= ddl;
           mu_floor = fmax(o.mu_min, fmin(o.tol, o.compl_inf_tol * df) / (o.barrier_tol_factor + 1.0));
@@ -1584,16 +1516,16 @@ struct WarpSolver {
             ws.misc()[lane] = l;
             ws.misc()[kNumRows + lane] = h;
           }
-          sync();
+          syncwarp();
         } else {
-          if (!cur_finite) { status = kInvalidNumber; return true; }
+          if (!cur_finite) { status = kInvalidNumber; break; }
           bool done = false;
           {
             const Errors e = compute_errors();
             const double E0 = e.E(0.0), cmp0 = e.compl_inf(0.0);
             const double viol = e.viol;
-            if (bo.trace && lane == 0) {
-              double* tr = bo.trace + ((size_t)pb * trace_rows + it) * kTraceCols;
+            if (out.trace && lane == 0) {
+              double* tr = out.trace + (size_t)it * kTraceCols;
               tr[0] = fval / df; tr[1] = E0; tr[2] = e.pr_inf; tr[3] = e.dual_inf;
               tr[4] = cmp0; tr[5] = mu; tr[6] = last_alpha; tr[7] = last_dw;
             }
@@ -1646,7 +1578,7 @@ struct WarpSolver {
               filt_n = 0;
             }
           }
-          if (done) return true;
+          if (done) break;
           dw = 0.0;
         }
       }
@@ -1660,7 +1592,7 @@ struct WarpSolver {
 #pragma unroll 1
         while (true) {
           write_row_terms(mode, dwu, rdv, cv);
-          sync();
+          syncwarp();
           ok = kkt_solve(dwu);
           if (ok || phase != kPhNewton) break;
           // inertia correction (IPOPT's PDPerturbationHandler schedule)
@@ -1673,7 +1605,7 @@ struct WarpSolver {
           if (dw > o.delta_w_max) { failed = true; break; }
           dwu = dw;
         }
-        if (failed) { status = kErrorInStepComputation; return true; }
+        if (failed) { status = kErrorInStepComputation; break; }
         double gs_ds, th_loc;
         const double a_new = slack_steps(rdv, dwu, gs_ds, th_loc);     // dsr = J_d dx + rdv ; FTB step
         if (phase == kPhInit) {
@@ -1688,7 +1620,7 @@ struct WarpSolver {
             ymax = fmax(ymax, fabs(R.yd[r]));
           }
           for (int a = 0; a < 7; ++a) { y0[a] = ok ? -newy0[a] : 0.0; ymax = fmax(ymax, fabs(y0[a])); }
-          ymax = wmax(ymax);
+          ymax = warp_max(ymax);
           if (!ok || !(ymax <= o.constr_mult_init_max)) {
             for (int a = 0; a < 6; ++a) lam[a] = 0.0;
             for (int a = 0; a < 7; ++a) y0[a] = 0.0;
@@ -1708,7 +1640,7 @@ struct WarpSolver {
           // grad(phi)' d
           double g = gs_ds;
           {
-            const double dup1 = shf(du[1], prev_lane());
+            const double dup1 = shfl(du[1], prev_lane());
             if (act && in_resto()) {
               const double d9[9] = {dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dsh, du[0], du[1]};
 #pragma unroll 1
@@ -1719,8 +1651,8 @@ struct WarpSolver {
               if (lane >= 1) g += 2.0 * prm().beta_delta * df * sigc_prev * (du[1] - dup1);
             }
           }
-          gpd = wsum(g);
-          theta = wsum(th_loc);
+          gpd = warp_sum(g);
+          theta = warp_sum(th_loc);
           phi = fval + mu * barB;
           if (gpd < 0.0) {
             amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gpd));
@@ -1745,9 +1677,9 @@ struct WarpSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; return false; }
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
-              return true;
+              break;
             }
           } else {
             a_soc = a_new;
@@ -1783,15 +1715,15 @@ struct WarpSolver {
           }
           reinit = true;           // least-squares multipliers at the restored point, then resume
           phase = kPhInit;
-          return false;
+          continue;
         }
-        if (resto_it >= o.resto_max_iter) { status = kRestorationNeeded; return true; }
+        if (resto_it >= o.resto_max_iter) { status = kRestorationNeeded; break; }
         phase = kPhNewton;
-        return false;
+        continue;
       }
       if (phase == kPhInit && reinit) {
         phase = kPhInit2;          // the slacks of the restored point are kept
-        return false;
+        continue;
       }
       if (phase == kPhInit) {
         // slacks pushed into their (relaxed) bounds; tp.rd holds the row values (s was 0)
@@ -1813,7 +1745,7 @@ struct WarpSolver {
           R.s[r] = v;
         }
         phase = kPhInit2;
-        return false;
+        continue;
       }
       if (phase == kPhInit2) {
         for (int k = 0; k < 6; ++k) cres[k] = tp.c[k];
@@ -1828,7 +1760,7 @@ struct WarpSolver {
         }
         reinit = false;
         phase = kPhNewton;
-        return false;
+        continue;
       }
       // ---- acceptance test of the trial point (plain or SOC step) --------------------------------
       n_ls += (phase == kPhSoc) ? 0 : 1;
@@ -1863,9 +1795,9 @@ struct WarpSolver {
             alpha *= o.alpha_red_factor;
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; return false; }
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
-              return true;
+              break;
             }
           } else {
             th_old = tp.theta;
@@ -1873,7 +1805,7 @@ struct WarpSolver {
 #pragma unroll 1
             for (int r = 0; r < kNumRows; ++r) d_soc[r] = a_soc * d_soc[r] + tp_rd[r];
           }
-          return false;
+          continue;
         }
         // plain step rejected: second-order correction on the first trial, else backtrack
         if (!soc_done && n_ls == 1 && tp.finite && tp.theta >= theta && o.max_soc > 0) {
@@ -1895,16 +1827,16 @@ struct WarpSolver {
             sv_dsr[r] = R.dsr[r];
           }
           phase = kPhSoc;
-          return false;
+          continue;
         }
         alpha *= o.alpha_red_factor;
         phase = kPhBacktrack;
         if (!(alpha >= amin && n_ls < 60)) {
-              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; return false; }
+              if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
-              return true;
+              break;
             }
-        return false;
+        continue;
       }
       // ================= E. accept the trial point ===============================================
       if (!f_type) filter_add((1.0 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);
@@ -1931,7 +1863,7 @@ struct WarpSolver {
           if (b < 0.0) az = fmin(az, -tau * c.vU * rcp_pivot(b));
         }
       }
-      az = wmin(az);
+      az = warp_min(az);
       for (int a = 0; a < 6; ++a) {
         x[a] = tp.x[a];
         cres[a] = tp.c[a];
@@ -1977,62 +1909,9 @@ struct WarpSolver {
       if (in_resto()) resto_it++;
       phase = in_resto() ? kPhRestoCheck : kPhNewton;
     }
-    return false;
-  }
 
-  // Inputs of problem b -> shared memory (one copy for the lane group), output pointers, lam_g cleared.
-  MPCR_D void load_problem(const BatchIn& in, int b) {
-    sync();                       // the previous problem of this lane group is done with the workspace
-    if (lane == 0) {
-      ProblemView pv;
-      for (int k = 0; k < 6; ++k) pv.x0[k] = in.x0[(size_t)b * 6 + k];
-      pv.u_prev[0] = in.u_prev[(size_t)b * 2 + 0];
-      pv.u_prev[1] = in.u_prev[(size_t)b * 2 + 1];
-      pv.has_prev_thr = pv.u_prev[0] == pv.u_prev[0];   // NaN = None (control/MPC.py:145-149)
-      pv.has_prev_st = pv.u_prev[1] == pv.u_prev[1];
-      pv.s0 = in.s0[b];
-      for (int k = 0; k < 5; ++k) { pv.cx[k] = in.cx[(size_t)b * 5 + k]; pv.cy[k] = in.cy[(size_t)b * 5 + k]; }
-      pv.max_err = in.max_err ? in.max_err[b] : 0.0;
-      pv.u_warm = in.u_warm ? in.u_warm + (size_t)b * 2 * N : nullptr;
-      if (!pv.has_prev_thr) pv.u_prev[0] = 0.0;
-      if (!pv.has_prev_st) pv.u_prev[1] = 0.0;
-      Params pr = cfg.p;
-      if (in.params) {
-        const double* q = in.params + (size_t)b * 5;
-        pr.alpha_c = q[0];
-        pr.d_max = q[1];
-        pr.q_v_y = q[2];
-        pr.n_exp = (int)(q[3] + 0.5);
-        pr.beta_delta = q[4];
-      }
-      *reinterpret_cast<Params*>(ws.prm_mem()) = pr;
-      *reinterpret_cast<ProblemView*>(ws.pb_mem()) = pv;
-    }
-    pb = b;
-    if (bo.lam_g) {
-      const int ls = lam_g_stride(cfg);
-      double* lg = bo.lam_g + (size_t)b * ls;
-      for (int k = lane; k < ls; k += W) lg[k] = 0.0;
-    }
-    // the always-zero slot of every stage record
-    for (int k = lane; k <= N; k += W) ws.st(k)[kOffZero] = 0.0;
-    sync();
-  }
-
-  // ---- outputs ---------------------------------------------------------------------------
-  MPCR_D void write_outputs() {
+    // ---- outputs ---------------------------------------------------------------------------
     {
-      const size_t b = (size_t)pb;
-      SolveOut out;
-      out.U = bo.U + b * 2 * N;
-      out.X = bo.X + b * 6 * (N + 1);
-      out.S = bo.S + b * (N + 1);
-      out.eC = bo.eC + b * N;
-      out.eL = bo.eL + b * N;
-      out.lam_g = bo.lam_g ? bo.lam_g + b * lam_g_stride(cfg) : nullptr;
-      out.obj = bo.obj + b;
-      out.status = bo.status + b;
-      out.iters = bo.iters + b;
       double xp[6], shp, up[2];
       gather_prev(x, sh, u, xp, shp, up);
       Poly4 px, py;
@@ -2087,66 +1966,112 @@ struct WarpSolver {
 };
 
 // ---------------------------------------------------------------------------
-// Kernel body: every lane group (warp, or half-warp when HALF) drains the batch's work queue -
-// fetch a problem, set it up, iterate to termination, store the outputs, fetch the next.  With
-// HALF the two groups of a warp run the SAME phase loop side by side: the loop re-converges the
-// warp at its top, a group that has nothing left waits in kPhExit until the other one is done.
+// One problem of a batch: load inputs, run the solver, store the outputs.
+// Called by every lane of a warp with the same arguments.
 // ---------------------------------------------------------------------------
+MPCR_HD int lam_g_stride(const Config& c) {
+  return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
+}
+
+template <int MODEL, bool RESTO = false, int IG = 0>
+MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
+                          int trace_rows, double* wsbase) {
+  const int N = cfg.N;
+  ProblemView pv;
+  for (int k = 0; k < 6; ++k) pv.x0[k] = in.x0[(size_t)b * 6 + k];
+  pv.u_prev[0] = in.u_prev[(size_t)b * 2 + 0];
+  pv.u_prev[1] = in.u_prev[(size_t)b * 2 + 1];
+  pv.has_prev_thr = pv.u_prev[0] == pv.u_prev[0];   // NaN = None (control/MPC.py:145-149)
+  pv.has_prev_st = pv.u_prev[1] == pv.u_prev[1];
+  pv.s0 = in.s0[b];
+  for (int k = 0; k < 5; ++k) { pv.cx[k] = in.cx[(size_t)b * 5 + k]; pv.cy[k] = in.cy[(size_t)b * 5 + k]; }
+  pv.max_err = in.max_err ? in.max_err[b] : 0.0;
+  pv.u_warm = in.u_warm ? in.u_warm + (size_t)b * 2 * N : nullptr;
+  if (!pv.has_prev_thr) pv.u_prev[0] = 0.0;
+  if (!pv.has_prev_st) pv.u_prev[1] = 0.0;
+  Params prm = cfg.p;
+  if (in.params) {
+    const double* q = in.params + (size_t)b * 5;
+    prm.alpha_c = q[0];
+    prm.d_max = q[1];
+    prm.q_v_y = q[2];
+    prm.n_exp = (int)(q[3] + 0.5);
+    prm.beta_delta = q[4];
+  }
+  SolveOut so;
+  so.U = out.U + (size_t)b * 2 * N;
+  so.X = out.X + (size_t)b * 6 * (N + 1);
+  so.S = out.S + (size_t)b * (N + 1);
+  so.eC = out.eC + (size_t)b * N;
+  so.eL = out.eL + (size_t)b * N;
+  so.lam_g = out.lam_g ? out.lam_g + (size_t)b * lam_g_stride(cfg) : nullptr;
+  so.obj = out.obj + b;
+  so.status = out.status + b;
+  so.iters = out.iters + b;
+  so.trace = out.trace ? out.trace + (size_t)b * trace_rows * kTraceCols : nullptr;
+  if (so.lam_g) {
+    const int ls = lam_g_stride(cfg);
+    for (int k = lane_id(); k < ls; k += 32) so.lam_g[k] = 0.0;
+    syncwarp();
+  }
+  RowState rows;
+  WarpSolver<MODEL, RESTO, IG> solver(cfg, rows, wsbase);
+  syncwarp();                       // the previous problem of this warp is done with the workspace
+  if (lane_id() == 0) {
+    *reinterpret_cast<Params*>(solver.ws.prm_mem()) = prm;
+    *reinterpret_cast<ProblemView*>(solver.ws.pb_mem()) = pv;
+  }
+  for (int k = lane_id(); k <= N; k += 32) solver.ws.st(k)[kOffZero] = 0.0;   // the always-zero slot of every stage record
+  syncwarp();
+  solver.solve(so);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel body: the warp drains the batch's work queue - fetch a problem, solve it, fetch the next
+// (converged problems free their warp immediately).
+// ---------------------------------------------------------------------------
+#if defined(MPCR_EMU)
+MPCR_D int atomic_next(int* counter) { return (*counter)++; }
+#else
+MPCR_D int atomic_next(int* counter) { return atomicAdd(counter, 1); }
+#endif
+
 struct WorkQueue {
   int* counter;        // next position of the dispatch order
   const int* order;    // dispatch order or null (= index order)
   int B;
 };
 
-template <int MODEL, bool RESTO, int IG, bool HALF>
+template <int MODEL, bool RESTO, int IG>
 MPCR_D void solve_batch(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
                         const WorkQueue& q, double* wsbase) {
-  RowState rows;
-  WarpSolver<MODEL, RESTO, IG, HALF> s(cfg, rows, wsbase, out, trace_rows);
-  s.phase = kPhLoad;
   while (true) {
-    if (HALF) syncwarp(kFullMask);           // both problem streams step through the loop together
-    if (s.phase == kPhLoad) {
-      int b = 0;
-      if (s.lane == 0) {
-        b = atomic_next(q.counter);
-        if (q.order && b < q.B) b = q.order[b];   // dispatch order (schedule kernels); results do not depend on it
-      }
-      b = s.shf_i(b, 0);
-      if (b >= q.B) {
-        s.phase = kPhExit;
-      } else {
-        s.load_problem(in, b);
-        s.setup();
-      }
+    int b = 0;
+    if (lane_id() == 0) {
+      b = atomic_next(q.counter);
+      if (q.order && b < q.B) b = q.order[b];      // dispatch order (schedule kernels); results do not depend on it
     }
-    if (HALF ? warp_all<32>(kFullMask, s.phase == kPhExit) : (s.phase == kPhExit)) break;
-    if (s.phase != kPhExit && s.iterate()) {
-      s.write_outputs();
-      s.phase = kPhLoad;
-    }
+    b = shfl_i(b, 0);
+    if (b >= q.B) break;
+    solve_problem<MODEL, RESTO, IG>(cfg, in, out, b, trace_rows, wsbase);
+    syncwarp();
   }
 }
 
-template <bool RESTO, int IG, bool HALF>
+template <bool RESTO, int IG>
 MPCR_D void solve_batch_model(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
                               const WorkQueue& q, double* wsbase) {
-  if (cfg.model == kDynamic) solve_batch<kDynamic, RESTO, IG, HALF>(cfg, in, out, trace_rows, q, wsbase);
-  else if (cfg.model == kKinematic) solve_batch<kKinematic, RESTO, IG, HALF>(cfg, in, out, trace_rows, q, wsbase);
-  else solve_batch<kBlended, RESTO, IG, HALF>(cfg, in, out, trace_rows, q, wsbase);
+  if (cfg.model == kDynamic) solve_batch<kDynamic, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
+  else if (cfg.model == kKinematic) solve_batch<kKinematic, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
+  else solve_batch<kBlended, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
 }
 
 // host builds (tests/emu): runtime dispatch over every instantiation
-MPCR_D void solve_batch_any(const Config& cfg, bool half, const BatchIn& in, const BatchOut& out,
-                            int trace_rows, const WorkQueue& q, double* wsbase) {
+MPCR_D void solve_batch_any(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
+                            const WorkQueue& q, double* wsbase) {
   const bool rs = cfg.o.restoration != 0, ig = cfg.integrator != 0;
-  if (half) {
-    if (rs) { if (ig) solve_batch_model<true, 1, true>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<true, 0, true>(cfg, in, out, trace_rows, q, wsbase); }
-    else { if (ig) solve_batch_model<false, 1, true>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<false, 0, true>(cfg, in, out, trace_rows, q, wsbase); }
-  } else {
-    if (rs) { if (ig) solve_batch_model<true, 1, false>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<true, 0, false>(cfg, in, out, trace_rows, q, wsbase); }
-    else { if (ig) solve_batch_model<false, 1, false>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<false, 0, false>(cfg, in, out, trace_rows, q, wsbase); }
-  }
+  if (rs) { if (ig) solve_batch_model<true, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<true, 0>(cfg, in, out, trace_rows, q, wsbase); }
+  else { if (ig) solve_batch_model<false, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<false, 0>(cfg, in, out, trace_rows, q, wsbase); }
 }
 
 }  // namespace mpcr

@@ -33,7 +33,8 @@ class RolloutSession:
 class ClosedLoopRollouts:
     def __init__(self, centerline, N=15, Ts=0.05, nlp_model="dynamic", plant="blended",
                  lookahead=45.0, lookback=5.0, window=2.0, device=0, runtime_params=None,
-                 restoration=False, estimate_state=False, start_control_at=0, use_graph=True):
+                 restoration=False, estimate_state=False, start_control_at=0, use_graph=True,
+                 solve_kernel="auto"):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
@@ -46,7 +47,7 @@ class ClosedLoopRollouts:
         self.start_control_at = int(start_control_at)    # agent.py:66 (the agent waits 50 ticks)
         self.use_graph = bool(use_graph)
         self.solver = BatchedMPC(N=N, Ts=Ts, model=nlp_model, device=device, on_device=True,
-                                 runtime_params=runtime_params, restoration=restoration)
+                                 runtime_params=runtime_params, restoration=restoration, solve_kernel=solve_kernel)
         self.lib = self.solver.lib
         self.track = centerline.device_track(self.solver)
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -150,6 +151,11 @@ class ClosedLoopRollouts:
         after = S.counters.cpu().numpy()
         return dict(converged_solves=int(after[2] - before[2]), finished=int(after[1]), travelled=S.travelled,
                     tick=int(after[0]))
+
+    def converged_so_far(self, S):
+        """Converged solves of unfinished vehicles since begin() (one small device -> host read)."""
+        self.stream.synchronize()
+        return int(S.counters[2].item())
 
     def fetch_bytes(self, R):
         return R * (8 * (1 + 1 + 1 + 6) + 4 * 2)

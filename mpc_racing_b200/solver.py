@@ -76,8 +76,8 @@ class BatchedMPC:
         cfg.d_max = float(rp.d_max if honor_instance_d_max else RuntimeControllerParameters.d_max)
         cfg.tol = float(tol)
         cfg.acceptable_tol = float(acceptable_tol)
-        # layout: 0 = auto, 1 = one problem per warp, 2 = two problems per warp (horizons up to 16)
-        cfg.solve_kernel = int({"auto": 0, "warp": 1, "half": 2}.get(solve_kernel, solve_kernel))
+        # layout: 0 = auto, 1 = one problem per warp (the only layout)
+        cfg.solve_kernel = int({"auto": 0, "warp": 1}.get(solve_kernel, solve_kernel))
         # "euler" = the reference's discretisation; "rk4" = extension (same kernel, 32-entry stage Jacobian)
         cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
         cfg.restoration = int(bool(restoration))     # feasibility restoration phase; off = status -2 instead

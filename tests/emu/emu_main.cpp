@@ -13,14 +13,13 @@ struct Job {
   const mpcr::BatchIn* in;
   const mpcr::BatchOut* out;
   mpcr::WorkQueue q;
-  bool half;
   int trace_rows;
   double* ws;
 };
 // every fiber (= lane) runs the kernel body; the warp drains the whole batch through the work queue
 void lane_body(void* p) {
   Job* j = (Job*)p;
-  mpcr::solve_batch_any(*j->cfg, j->half, *j->in, *j->out, j->trace_rows, j->q, j->ws);
+  mpcr::solve_batch_any(*j->cfg, *j->in, *j->out, j->trace_rows, j->q, j->ws);
 }
 }  // namespace
 
@@ -32,8 +31,6 @@ extern "C" int emu_lam_g_stride(const mpcr_config* c) {
 
 extern "C" void emu_config_default(mpcr_config* c) { mpcr::config_default(c); }
 
-// solve_kernel = MPCR_KERNEL_HALFWARP runs the two-problems-per-warp layout, anything else one
-// problem per warp
 extern "C" int emu_solve_batch(const mpcr_config* c, int B, const double* x0, const double* u_prev,
                                const double* s0, const double* cx, const double* cy,
                                const double* max_err, const double* params, const double* u_warm,
@@ -46,10 +43,9 @@ extern "C" int emu_solve_batch(const mpcr_config* c, int B, const double* x0, co
   mpcr::config_convert(*c, &cfg);
   mpcr::BatchIn in{x0, u_prev, s0, cx, cy, max_err, params, u_warm};
   mpcr::BatchOut out{U, X, S, eC, eL, lam_g, obj, status, iters, trace};
-  const bool half = c->solve_kernel == MPCR_KERNEL_HALFWARP;
-  std::vector<double> ws((half ? 2 : 1) * mpcr::ws_doubles(cfg.N, cfg.integrator));
+  std::vector<double> ws(mpcr::ws_doubles(cfg.N, cfg.integrator));
   int counter = 0;
-  Job j{&cfg, &in, &out, mpcr::WorkQueue{&counter, nullptr, B}, half, cfg.o.max_iter + 1, ws.data()};
+  Job j{&cfg, &in, &out, mpcr::WorkQueue{&counter, nullptr, B}, cfg.o.max_iter + 1, ws.data()};
   emu::run_warp(lane_body, &j);
   return 0;
 }

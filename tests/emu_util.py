@@ -40,14 +40,10 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def emu_solve(x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None, trace=False, half=False,
-              **cfg_kw):
-    """half=True: the two-problems-per-warp layout (horizons up to 16)."""
+def emu_solve(x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None, trace=False, **cfg_kw):
     lib = emu_lib()
     cfg = MpcrConfig()
     lib.emu_config_default(C.byref(cfg))
-    if half:
-        cfg.solve_kernel = 2
     for k, v in cfg_kw.items():
         assert hasattr(cfg, k), k
         setattr(cfg, k, v)

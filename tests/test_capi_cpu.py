@@ -78,14 +78,13 @@ def test_no_product_import_of_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
 
 
-def test_halfwarp_layout_needs_a_short_horizon(lib):
-    """solve_kernel = HALFWARP (two problems per warp) with N > 16 is rejected at create time (the
-    config check runs before any device is touched)."""
+def test_unknown_layout_is_rejected(lib):
+    """solve_kernel values other than AUTO / WARP are rejected at create time (the config check
+    runs before any device is touched)."""
     import ctypes as C
     from mpc_racing_b200 import _capi
     cfg = _capi.default_config(lib)
     assert cfg.integrator == 0 and cfg.solve_kernel == 0 and cfg.polish_tol == 0.0
     cfg.solve_kernel = 2
-    cfg.N = 17
     h = C.c_void_p()
     assert lib.mpcr_create(C.byref(cfg), C.byref(h)) == -1      # MPCR_ERR_INVALID_ARG

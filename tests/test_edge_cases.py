@@ -16,13 +16,12 @@ def cfg2():
 
 
 # ---- CPU: the kernel sources compiled for the host (tests/emu) and the config checks ----------
-@pytest.mark.parametrize("N,half", [(2, False), (2, True), (16, True), (32, False)])
-def test_horizon_limits(cfg2, N, half):
-    """N = 2 (smallest), N = 16 (the largest the half-warp layout holds) and N = 32 (one warp lane per
-    stage: the largest) against the oracle."""
+@pytest.mark.parametrize("N", [2, 32])
+def test_horizon_limits(cfg2, N):
+    """N = 2 (smallest) and N = 32 (one warp lane per stage: the largest) against the oracle."""
     from emu_util import emu_solve
     i = [7]
-    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], N=N, half=half)
+    out = emu_solve(cfg2['x0'][i], cfg2['u_prev'][i], cfg2['s0'][i], cfg2['cx'][i], cfg2['cy'][i], N=N)
     ref = oracle_solve(cfg2['x0'][7], cfg2['u_prev'][7], cfg2['s0'][7], cfg2['cx'][7], cfg2['cy'][7], N=N)
     assert_parity(out, 0, ref)
 
@@ -50,8 +49,8 @@ def test_invalid_config_is_rejected(field, value):
     assert not h
 
 
-@pytest.mark.parametrize("N,half", [(30, False), (15, True)])
-def test_pathological_inputs_terminate_with_failure_codes(cfg2, N, half):
+@pytest.mark.parametrize("N", [30, 15])
+def test_pathological_inputs_terminate_with_failure_codes(cfg2, N):
     """NaN / Inf / singular inputs never hang or poison neighbours: each problem ends with a failure
     status (control/MPC.py:172-181 convention: last iterate, sol = None)."""
     from emu_util import emu_solve
@@ -63,7 +62,7 @@ def test_pathological_inputs_terminate_with_failure_codes(cfg2, N, half):
     x0[4, 3] = 0.0
     x0[4, 4] = 0.0                     # |v| = 0: the steering-gain derivative divides by it
     s0[5] = 1e9                        # absurd progress
-    r = emu_solve(x0, cfg2['u_prev'][idx], s0, cx, cfg2['cy'][idx], N=N, half=half, max_iter=60)
+    r = emu_solve(x0, cfg2['u_prev'][idx], s0, cx, cfg2['cy'][idx], N=N, max_iter=60)
     assert list(r['status'][:3]) == [-4, -4, -4]            # Invalid_Number_Detected
     assert r['status'][3] == 0                               # the untouched neighbour converges
     assert r['status'][4] < 0 and r['status'][5] < 0

@@ -1,9 +1,8 @@
 """GPU fuzz: the CUDA solver against the independent compiled CPU oracle (oracle/cxx: AD derivatives,
-block-tridiagonal LDL^T) and, for horizons up to 16, its two lane layouts against each other, over
-random configurations - horizon, step, model, lane row, wrap rows, restoration, NaN previous inputs,
+block-tridiagonal LDL^T) over random configurations - horizon, step, model, lane row, wrap rows, restoration, NaN previous inputs,
 per-problem controller parameters (well outside the reference's ranges: badly scaled objectives),
 warm starts.  Success / failure must agree problem by problem; where the iteration counts agree the
-objectives agree to round-off; the two layouts are bit-identical."""
+objectives agree to round-off."""
 import numpy as np
 import pytest
 
@@ -76,7 +75,3 @@ def test_kernel_agrees_with_the_compiled_oracle_on_random_configurations():
         assert m["class_eq"] >= 0.97, ctx            # success / failure, problem by problem
         assert m["worst_same"] <= 1e-7, ctx          # same iteration count => same result
         assert m["obj_close"] >= 0.95, ctx
-        if kw["N"] <= 16:
-            h = BatchedMPC(solve_kernel="half", **kw).solve(*args, **opt)
-            for k in ("U", "X", "S", "lam_g", "obj", "status", "iters"):
-                assert np.array_equal(getattr(a, k), getattr(h, k), equal_nan=True), (ctx, k)

@@ -167,35 +167,6 @@ def test_dropin_mpc_class(cfg2):
     assert r1[0].shape == (6, 26) and np.isfinite(r1[0]).all()
 
 
-def test_halfwarp_layout_is_bit_identical_to_the_warp_layout():
-    """Two problems per warp (N <= 16, MPCR_KERNEL_HALFWARP) against one problem per warp: the same
-    arithmetic in the same order on 16 instead of 32 lanes, so every output is bit-identical -
-    for every model, with the lane row, the restoration build, RK4, ragged and odd batch sizes."""
-    from mpc_racing_b200.solver import BatchedMPC
-    d = load_fixture("prod_t4_256.npz")
-    d3 = load_fixture("cfg3_t1_triple_512.npz")
-    cases = [(d, 256, dict(N=15)), (d, 255, dict(N=15, model="blended")), (d, 1, dict(N=16, model="kinematic")),
-             (d, 77, dict(N=2)), (d, 64, dict(N=12, integrator="rk4")), (d, 96, dict(N=15, wrap_constraint=False)),
-             (d3, 200, dict(N=15, lane_constraint=True, restoration=True))]
-    for fx, B, kw in cases:
-        args = (fx['x0'][:B], fx['u_prev'][:B], fx['s0'][:B], fx['cx'][:B], fx['cy'][:B])
-        me = fx['max_err'][:B] if kw.get("lane_constraint") else None
-        w = BatchedMPC(Ts=0.05, solve_kernel="warp", **kw)
-        h = BatchedMPC(Ts=0.05, solve_kernel="half", **kw)
-        a = w.solve(*args, max_err=me)
-        b = h.solve(*args, max_err=me)
-        assert h.launch_info()["blocks"] == min((B + 1) // 2, h.launch_info()["blocks"])
-        for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters"):
-            assert np.array_equal(getattr(a, k), getattr(b, k)), (kw, B, k)
-    # AUTO: the half-warp layout once the batch exceeds one problem per resident warp
-    auto = BatchedMPC(N=15, Ts=0.05)
-    big = {k: np.tile(d[k], (8,) + (1,) * (d[k].ndim - 1)) for k in ('x0', 'u_prev', 's0', 'cx', 'cy')}
-    r = auto.solve(big['x0'], big['u_prev'], big['s0'], big['cx'], big['cy'])
-    assert auto.launch_info()["smem_bytes"] == 2 * BatchedMPC(N=15, Ts=0.05, solve_kernel="warp").launch_info()["smem_bytes"]
-    one = BatchedMPC(N=15, Ts=0.05, solve_kernel="warp").solve(d['x0'], d['u_prev'], d['s0'], d['cx'], d['cy'])
-    assert np.array_equal(r.U[:256], one.U) and np.array_equal(r.U[256:512], one.U)
-
-
 @pytest.mark.parametrize("name,kw,N", [("cfg2_shanghai_4096", {}, 30),
                                        ("cfg3_t1_triple_512", dict(lane_constraint=True), 30),
                                        ("cfg3_t1_triple_512_resto", dict(lane_constraint=True, restoration=True), 30),
