@@ -134,7 +134,9 @@ int mpcr_solve_batch(mpcr_handle* h, int B,
                      const double* cx      /* [B,5] */,
                      const double* cy      /* [B,5] */,
                      const double* max_err /* [B] or NULL */,
-                     const double* params  /* [B,5] alpha_c,d_max,q_v_y,n,beta_delta or NULL */,
+                     const double* params  /* [B,5] alpha_c,d_max,q_v_y,n,beta_delta or NULL; a row that is not finite,
+                                              has n < 1 (n is rounded to the nearest integer) or negative weights makes
+                                              that problem end with MPCR_INVALID_NUMBER, the others are unaffected */,
                      const double* u_warm  /* [B,2,N] or NULL */,
                      double* U             /* [B,2,N] */,
                      double* X             /* [B,6,N+1] */,

@@ -1997,6 +1997,14 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
     prm.q_v_y = q[2];
     prm.n_exp = (int)(q[3] + 0.5);
     prm.beta_delta = q[4];
+    // a row outside the accepted range poisons this problem only: the solver ends it with
+    // Invalid_Number_Detected (include/mpcr.h)
+    bool ok = true;
+    for (int k = 0; k < 5; ++k) ok = ok && (q[k] == q[k]) && fabs(q[k]) < 1.0e300;
+    if (!(ok && q[0] >= 0.0 && q[2] >= 0.0 && q[4] >= 0.0 && q[3] >= 0.5 && q[3] < 64.0)) {
+      prm.alpha_c = nan("");
+      prm.n_exp = 2;
+    }
   }
   SolveOut so;
   so.U = out.U + (size_t)b * 2 * N;

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0", "--batch", "256"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "converged_nmpc_solves_per_sec"
@@ -18,7 +18,8 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "solves/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"]
+    assert "workload" in line["config"] and line["config"]["batch_per_gpu"] == 256 and line["config"]["restoration"] is True
+    assert line["cpu_baseline"]["port"] == "oracle/cxx"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

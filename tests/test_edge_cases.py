@@ -120,3 +120,19 @@ def test_iteration_cap_and_horizons_on_gpu(cfg2):
         ref = oracle_solve(cfg2['x0'][7], cfg2['u_prev'][7], cfg2['s0'][7], cfg2['cx'][7], cfg2['cy'][7], N=N)
         assert_parity(dict(U=res.U, X=res.X, S=res.S, lam_g=res.lam_g, obj=res.obj, status=res.status,
                            iters=res.iters), 0, ref)
+
+
+def test_invalid_parameter_rows_poison_only_their_problem(cfg2):
+    """A per-problem parameter row outside the accepted range (include/mpcr.h: not finite, n < 1,
+    negative weights) ends THAT problem with Invalid_Number_Detected; its neighbours are untouched."""
+    from emu_util import emu_solve
+    idx = [0, 1, 2, 3]
+    good = np.array([1000.0, 0.85, 50.0, 2.0, 5000.0])
+    prm = np.tile(good, (4, 1))
+    prm[1, 3] = 0.0            # exponent 0
+    prm[2, 0] = np.nan         # NaN weight
+    prm[3, 4] = -1.0           # negative steer-rate weight
+    r = emu_solve(cfg2['x0'][idx], cfg2['u_prev'][idx], cfg2['s0'][idx], cfg2['cx'][idx], cfg2['cy'][idx], params=prm)
+    ref = emu_solve(cfg2['x0'][:1], cfg2['u_prev'][:1], cfg2['s0'][:1], cfg2['cx'][:1], cfg2['cy'][:1])
+    assert r['status'][0] == 0 and np.array_equal(r['U'][0], ref['U'][0])
+    assert list(r['status'][1:]) == [-4, -4, -4]

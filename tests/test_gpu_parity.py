@@ -172,14 +172,14 @@ def test_dropin_mpc_class(cfg2):
                                        ("cfg3_t1_triple_512_resto", dict(lane_constraint=True, restoration=True), 30),
                                        ("prod_t4_256", {}, 15)])
 def test_whole_batches_against_oracle_golden(name, kw, N):
-    """EVERY problem of BASELINE config 2 (4096), config 3 (512, lane rows) and the production
-    batch (256, N = 15) against the committed oracle solutions (tests/golden/*_oracle.npz,
-    generator make_oracle_solutions.py).  Kernel (Riccati) and oracle (dense LDL') follow the same
-    algorithm but not the same round-off, so a small fraction of paths separate; measured on B200
-    (gpurun golden_compare, DESIGN.md "Parity status"): status class equal 100 % / 99.8 % / 100 %,
-    objective within 1e-6 for 99.88 % / 99.4 % / 100 %, inputs within 1e-4 for 98.1 % / 97.1 % /
-    99.2 % - the rest are throttle components the tol = 1e-4 termination leaves undetermined at the
-    1e-3 level (objective still equal to 1e-6) and a handful of different local minima."""
+    """EVERY problem of BASELINE config 2 (4096), config 3 (512, lane rows, with and without the
+    restoration phase) and the production batch (256, N = 15) against the committed oracle solutions
+    (tests/golden/*_oracle.npz, generator make_oracle_solutions.py).  Kernel (Riccati + Woodbury) and
+    oracle (dense LDL') follow the same algorithm but not the same round-off.  Measured on B200, round 2
+    (tools/parity_report.py, DESIGN.md "Parity status"): converged / failed class equal 100 % on every
+    batch, objective within 1e-6 on 100 %, inputs within 1e-4 on 99.90 % / 100 % / 100 % / 100 % - the
+    config-2 rest are 4 problems (245, 910, 1622, 3231) with the objective equal to 1e-6 and one
+    throttle component off by up to 5.7e-3: a direction the tol = 1e-4 termination leaves undetermined."""
     import os
     from mpc_racing_b200.solver import BatchedMPC
     d = load_fixture(name.replace("_resto", "") + ".npz")
@@ -188,20 +188,43 @@ def test_whole_batches_against_oracle_golden(name, kw, N):
         assert (g["status"] >= 0).all()      # with the restoration phase the oracle solves all 512
     r = BatchedMPC(N=N, Ts=0.05, **kw).solve(d["x0"], d["u_prev"], d["s0"], d["cx"], d["cy"],
                                             max_err=d["max_err"] if kw else None)
-    assert ((r.status >= 0) == (g["status"] >= 0)).mean() >= 0.995
-    assert (r.status == g["status"]).mean() >= 0.99
+    n = len(g["status"])
+    assert ((r.status >= 0) != (g["status"] >= 0)).sum() <= 1          # measured: 0
+    assert (r.status != g["status"]).sum() <= 2                        # measured: 1 (-3 vs -2), 0, 0, 0
     both = (r.status >= 0) & (g["status"] >= 0)
     rel = (np.abs(r.obj - g["obj"]) / np.abs(g["obj"]))[both]
-    assert (rel <= 1e-6).mean() >= 0.99, (rel <= 1e-6).mean()
+    assert (rel > 1e-6).sum() <= 1, np.where(rel > 1e-6)[0]            # measured: 0 - no different minima
     dU = np.abs(r.U - g["U"]) / np.maximum(1.0, np.abs(g["U"]))
     dU[:, 0, -1] = 0.0
     du = dU.reshape(len(dU), -1).max(axis=1)[both]
-    assert (du <= 1e-4).mean() >= 0.96, (du <= 1e-4).mean()
-    # where the objective agrees, steering agrees and what is left are isolated throttle components
-    # along which the objective is flat at the termination tolerance
-    ok = rel <= 1e-6
-    assert dU[:, 1].reshape(len(dU), -1).max(axis=1)[both][ok].max() <= 3e-3      # measured: <= 1.1e-3
-    assert np.percentile(du[ok], 99) <= 1e-3, np.percentile(du[ok], 99)          # measured: <= 4e-4
+    assert (du > 1e-4).sum() <= max(2, n // 500), np.where(du > 1e-4)[0]     # measured: 4 of 4096, else 0
+    assert du.max() <= 1e-2                                            # measured: 5.7e-3
+    assert (r.iters == g["iters"]).mean() >= 0.95                      # measured: 97.3 - 99.6 %
+
+
+def test_polished_solutions_agree_with_the_compiled_oracle(cfg2):
+    """The tol-polish argument made testable: kernel and compiled oracle both continue
+    to 1e-9 after their tol = 1e-4 termination; every config-2 problem on which both converge to the
+    same minimum (measured: all 4095 converged ones) then agrees to 2e-4 in the inputs and 1e-6 in the
+    objective, 99.9 % to 1e-4 (measured: one problem, 3981, at 1.15e-4), with status and iteration
+    count of the FIRST termination unchanged."""
+    from mpc_racing_b200.solver import BatchedMPC
+    from oracle import cxx
+    args = (cfg2['x0'], cfg2['u_prev'], cfg2['s0'], cfg2['cx'], cfg2['cy'])
+    plain = BatchedMPC(N=30, Ts=0.05).solve(*args)
+    r = BatchedMPC(N=30, Ts=0.05, polish_tol=1e-9).solve(*args)
+    assert np.array_equal(r.status, plain.status) and np.array_equal(r.iters, plain.iters)
+    c = cxx.solve_batch(*args, polish_tol=1e-9)
+    assert ((r.status >= 0) == (c["status"] >= 0)).all()
+    both = (r.status >= 0) & (c["status"] >= 0)
+    rel = np.abs(r.obj - c["obj"]) / np.abs(c["obj"])
+    same_min = both & (rel <= 1e-6)
+    assert same_min.sum() >= both.sum() - 1                            # measured: no different minimum
+    dU = np.abs(r.U - c["U"]) / np.maximum(1.0, np.abs(c["U"]))
+    dU[:, 0, -1] = 0.0
+    du = dU.reshape(len(dU), -1).max(axis=1)
+    assert du[same_min].max() <= 2e-4, (du[same_min].max(), np.where(same_min & (du > 1e-4))[0])
+    assert (du[same_min] <= 1e-4).mean() >= 0.999
 
 
 def test_rk4_integrator_on_gpu(cfg2):
