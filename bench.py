@@ -58,6 +58,8 @@ def flop_per_iter(N):
 
 def config_block(name, cfg, batch_per_gpu, scaling, inner=None):
     """The keys both arms print under "config" (identical in the two arms)."""
+    if cfg["kind"] == "ga":
+        scaling = "strong"               # population x tracks is a fixed job, sharded over the ranks
     c = {"workload": cfg["workload"], "name": name, "batch_per_gpu": batch_per_gpu, "N": cfg["N"], "Ts": TS,
          "model": cfg["model"], "lane_rows": bool(cfg.get("lane", False)), "restoration": True,
          "scaling": scaling}
@@ -118,8 +120,18 @@ def pin_to_gpu_numa(local):
 # ---------------------------------------------------------------------------------------
 # CPU arm: the compiled oracle (oracle/cxx) - bench.py's cpu_baseline leg and --impl reference
 # ---------------------------------------------------------------------------------------
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm asks for
+    its threads explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cxx_solve(batch, cfg, threads=0):
     from oracle import cxx
+    threads = threads or host_cores()
     t0 = time.perf_counter()
     r = cxx.solve_batch(batch["x0"], batch["u_prev"], batch["s0"], batch["cx"], batch["cy"], N=cfg["N"], Ts=TS,
                         model=cfg["model"], lane=cfg.get("lane", False),
@@ -188,7 +200,7 @@ class CpuClosedLoop:
                 cx[r] = self.cl.x_as_coeffs(prog[r] - 5, 45, 4)
                 cy[r] = self.cl.y_as_coeffs(prog[r] - 5, 45, 4)
             res = cxx.solve_batch(x, u_prev, prog, cx, cy, N=self.cfg["N"], Ts=TS, model=self.cfg["model"],
-                                  params=params, u_warm=u_warm, restoration=True)
+                                  params=params, u_warm=u_warm, restoration=True, threads=host_cores())
             conv += int((res["status"] >= 0).sum())
             u0 = res["U"][:, :, 0]
             for r in range(R):
@@ -226,7 +238,7 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B = args.batch if args.scaling == "weak" else max(1, args.batch // max(1, world))
     conv = 0
@@ -277,7 +289,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": conf["scaling"], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": conf,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "port": "oracle/cxx",
                          "sample": sample},
@@ -461,7 +473,7 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         pass
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         conv, dt = cxx_solve(host, cfg)
         cpu = {"value": conv / dt, "unit": UNIT, "cores": cores, "kind": "port", "port": "oracle/cxx",
                "sample": f"rank 0's whole batch ({B} problems, same options), oracle/cxx (C++17 + OpenMP, "
@@ -613,7 +625,6 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
     ranks = {n: {"min": float(per_rank[:, i].min()), "median": float(np.median(per_rank[:, i])),
                  "max": float(per_rank[:, i].max()), "per_rank": [float(v) for v in per_rank[:, i]]}
              for i, n in enumerate(names)}
-    step_ms = total_ms_max / args.steps / K / max(1, len(engines))
     N = cfg["N"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -625,7 +636,7 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
                     "restoration phase ON",
         "detail": {"rollouts_all_ranks": n_all, "control_steps_per_sec": n_all * K * args.steps / (total_ms_max * 1e-3),
                    "converged_frac": conv_all / (n_all * K * args.steps),
-                   "ms_per_control_step_per_track": step_ms, "solve_kernel_share": solve_ms / step_ms if step_ms else None,
+                   "ms_per_control_step": total_ms_max / args.steps / K,
                    "tracks": [e["track"] for e in engines], "host_affinity": pinned,
                    "fitness_vector": None if fit_local is None else int(fit_local.numel())},
         "clocks": summarize_clocks(samples),
@@ -635,7 +646,8 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
         "roofline": {"bound": "fp64", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
                      "traffic": None, "kernel": "mpcr::solve_kernel",
                      "kernel_ms": solve_ms,
-                     "note": "iteration counts are not read back inside the loop; see the cfg2 line for the roofline"},
+                     "note": "kernel_ms = the last UNGRAPHED tick's solve (graph replays carry no timing events); "
+                             "iteration counts are not read back inside the loop; see the cfg2 line for the roofline"},
         "ranks": ranks,
         "cpu_baseline": None,
     }

@@ -102,11 +102,17 @@ def test_agent_state_estimate_and_warmup(t4):
     (agent.py:240-254: yaw rate by finite difference of the wrapped yaw, velocities world -> body)
     and its open-loop warm-up (agent.py:278-283: throttle 0.5, steer 0 before start_control_at)."""
     from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
-    R, K, W = 16, 12, 5
+    R, K, W = 16, 16, 5
     ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="blended", estimate_state=True, start_control_at=W)
-    x0, s0 = start_states(t4, R, seed=3, v0=12.0)
-    x0[:, 2] = np.where(np.arange(R) % 2 == 0, 3.1, x0[:, 2])       # half of the fleet crosses yaw = pi
-    x0[:, 5] = 0.4
+    # start the fleet 0.3 ... 5 m before the point where the track heading crosses +-pi, at 8 m/s:
+    # every vehicle's (wrapped) plant yaw jumps by 2 pi within the K ticks
+    sg = np.linspace(0.0, t4.length, 4000, endpoint=False)
+    eg = t4.eval_all(sg)
+    yg = np.arctan2(eg[:, 3], eg[:, 2])
+    s_star = sg[np.where(np.abs(np.diff(yg)) > 3)[0][0]]
+    s0 = (s_star - np.linspace(0.3, 5.0, R)) % t4.length
+    e = t4.eval_all(s0)
+    x0 = np.stack([e[:, 0], e[:, 1], np.arctan2(e[:, 3], e[:, 2]), np.full(R, 8.0), np.zeros(R), np.zeros(R)], axis=1)
     hist = ro.run(x0, s0, max_steps=K, record=True)["history"]
     xp = x0.copy()
     wraps = 0
@@ -133,7 +139,9 @@ def test_agent_state_estimate_and_warmup(t4):
         if k < W:
             np.testing.assert_array_equal(hist[k]["u0"], np.tile([0.5, 0.0], (R, 1)))
         else:
-            assert (hist[k]["status"] >= 0).mean() >= 0.9
+            ok = hist[k]["status"] >= 0                                    # the MPC has taken over
+            assert ok.mean() >= 0.75, hist[k]["status"]
+            assert (np.abs(hist[k]["u0"][ok] - np.array([0.5, 0.0])).max(axis=1) > 0).any()
         yaw_old = yaw.copy()
         xp = hist[k]["x_plant_next"]
     assert wraps >= 1
