@@ -103,7 +103,9 @@ def test_agent_state_estimate_and_warmup(t4):
     and its open-loop warm-up (agent.py:278-283: throttle 0.5, steer 0 before start_control_at)."""
     from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
     R, K, W = 16, 16, 5
-    ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="blended", estimate_state=True, start_control_at=W)
+    # the dynamic plant: the reference's BLENDED plant mixes the two models' wrapped yaw angles linearly
+    # (models/BlendedBicycleModel.py:46), which yields a meaningless heading at the +-pi crossing
+    ro = ClosedLoopRollouts(t4, N=15, Ts=0.05, plant="dynamic", estimate_state=True, start_control_at=W)
     # start the fleet 0.3 ... 5 m before the point where the track heading crosses +-pi, at 8 m/s:
     # every vehicle's (wrapped) plant yaw jumps by 2 pi within the K ticks
     sg = np.linspace(0.0, t4.length, 4000, endpoint=False)
@@ -135,16 +137,16 @@ def test_agent_state_estimate_and_warmup(t4):
             crossed = np.abs(yaw - yaw_old) > 3                        # the plant wraps its yaw into (-pi, pi]
             wraps += int(crossed.sum())
             # at a crossing the estimate is the small physical rate, not -+2 pi / Ts = 126 rad/s
-            assert (np.abs(seen[crossed, 5] - xp[crossed, 5]) < 2.0).all()
+            assert (np.abs(seen[crossed, 5] - xp[crossed, 5]) < 1.0).all(), (seen[crossed, 5], xp[crossed, 5])
         if k < W:
             np.testing.assert_array_equal(hist[k]["u0"], np.tile([0.5, 0.0], (R, 1)))
         else:
             ok = hist[k]["status"] >= 0                                    # the MPC has taken over
-            assert ok.mean() >= 0.75, hist[k]["status"]
-            assert (np.abs(hist[k]["u0"][ok] - np.array([0.5, 0.0])).max(axis=1) > 0).any()
+            assert ok.mean() >= 0.75, (k, hist[k]["status"])
+            assert (np.abs(hist[k]["u0"][ok] - np.array([0.5, 0.0])).max(axis=1) > 0).any(), k
         yaw_old = yaw.copy()
         xp = hist[k]["x_plant_next"]
-    assert wraps >= 1
+    assert wraps >= 1, "no vehicle crossed the heading wrap"
     ro.close()
 
 
