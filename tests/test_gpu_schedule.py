@@ -44,3 +44,30 @@ def test_schedule_with_degenerate_inputs():
     ok = ref.status >= 0
     assert ok.sum() >= n - 10
     assert np.array_equal(r.U[ok], ref.U[ok])
+
+
+def test_one_handle_from_two_streams_is_serialised_on_the_device():
+    """A handle owns one dispatch counter / order buffer / event pair (include/mpcr.h): launches from
+    different streams on the SAME handle are ordered on the device by the library (the second waits
+    for the first), so interleaving them cannot skip or double-solve problems."""
+    import torch
+    from mpc_racing_b200.solver import BatchedMPC
+    d = load_fixture("cfg2_shanghai_4096.npz")
+    dev = torch.device("cuda", 0)
+    s = BatchedMPC(N=30, Ts=0.05, on_device=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    A = [t(d[k][:1500]) for k in ("x0", "u_prev", "s0", "cx", "cy")]
+    B = [t(d[k][1500:3000]) for k in ("x0", "u_prev", "s0", "cx", "cy")]
+    ref_a, ref_b = s.solve(*A), s.solve(*B)
+    torch.cuda.synchronize()
+    ra, rb = ref_a.U.clone(), ref_b.U.clone()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    outs = []
+    for rep in range(3):
+        oa = s.solve(*A, stream=s1.cuda_stream)
+        ob = s.solve(*B, stream=s2.cuda_stream)
+        outs.append((oa, ob))
+    torch.cuda.synchronize()
+    for oa, ob in outs:
+        assert torch.equal(oa.U, ra) and torch.equal(ob.U, rb)
+        assert torch.equal(oa.iters, ref_a.iters) and torch.equal(ob.status, ref_b.status)

@@ -41,12 +41,18 @@ def cmp(a, b, tag):
                du_outliers_same_min=[int(i) for i in np.where(same_min & (du > 1e-4))[0]],
                status_differs=[(int(i), int(st_a[i]), int(st_b[i])) for i in np.where(st_a != st_b)[0][:16]],
                last_throttle_max=float(last[both].max()))
+    if "lam_g" in a and "lam_g" in b and a["lam_g"] is not None:
+        m = min(a["lam_g"].shape[1], b["lam_g"].shape[1])
+        den = np.maximum(1.0, np.abs(b["lam_g"][:, :m]).max(axis=1))
+        dl = np.abs(a["lam_g"][:, :m] - b["lam_g"][:, :m]).max(axis=1) / den
+        out["lam_g_within_1e4"] = float((dl[same_min] <= 1e-4).mean()) if same_min.any() else None
+        out["lam_g_max"] = float(dl[same_min].max()) if same_min.any() else None
     print(json.dumps(out), flush=True)
     return out
 
 
 def as_dict(r):
-    return dict(status=r.status, iters=r.iters, obj=r.obj, U=r.U)
+    return dict(status=r.status, iters=r.iters, obj=r.obj, U=r.U, lam_g=r.lam_g)
 
 
 for name, kw, okw, N in (("cfg2_shanghai_4096", {}, {}, 30),
