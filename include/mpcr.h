@@ -96,10 +96,14 @@ typedef struct mpcr_config {
   int32_t solve_kernel;      /* MPCR_KERNEL_* (0 = auto) */
   int32_t integrator;        /* MPCR_INTEGRATOR_EULER (reference, default) or MPCR_INTEGRATOR_RK4 (extension:
                               * the dynamics rows become x_i = RK4(x_{i-1}, u_{i-1}), same kernel) */
-  int32_t restoration;       /* 1: when the filter line search fails, run the feasibility-restoration phase
-                              * (IPOPT would; quadratic-penalty variant) instead of returning
-                              * MPCR_RESTORATION_FAILED.  Selects the kernel build that contains the phase
-                              * (~6 % slower per iteration).  0 = off (default) */
+  int32_t restoration;       /* when the filter line search fails, run the feasibility-restoration phase (IPOPT
+                              * would; quadratic-penalty variant) instead of returning
+                              * MPCR_RESTORATION_FAILED.  0 = off (default).  1 = two-stage: every problem runs
+                              * the plain solver and the few that need the phase are solved again, from the
+                              * start, by the build that carries it (no cost for the others).  2 = every
+                              * problem runs the build with the phase (~6 % slower per iteration; cheaper than
+                              * 1 once more than a few percent of a batch need the phase, e.g. lane rows).
+                              * 1 and 2 return the same solutions up to round-off. */
   int32_t schedule;          /* MPCR_SCHEDULE_*: order in which the persistent warps pick problems off the batch.
                               * Results do not depend on it; kernel time does (stragglers picked last leave
                               * the GPU idle).  0 = auto: expected-longest-first (reference-path curvature)

@@ -1,6 +1,6 @@
 """In-tree build of libmpcr.so (nvcc, sm_100a only).
 
-The solve kernel has 4 template variants (restoration x integrator, three models each); each is its own
+The solve kernel has 6 template variants (restoration mode x integrator, three models each); each is its own
 translation unit (csrc/mpcr_solve_variant.cu with -D flags) so that they compile in parallel.
 """
 import os
@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmpcr.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-VARIANTS = [(r, i) for r in (0, 1) for i in (0, 1)]
+VARIANTS = [(r, i) for r in (0, 1, 2) for i in (0, 1)]
 
 
 def _deps():

@@ -23,14 +23,17 @@
 
 namespace mpcr {
 
-template <> SolveKernelFn solve_kernel_table<false, 0>(int);
-template <> SolveKernelFn solve_kernel_table<false, 1>(int);
-template <> SolveKernelFn solve_kernel_table<true, 0>(int);
-template <> SolveKernelFn solve_kernel_table<true, 1>(int);
+template <> SolveKernelFn solve_kernel_table<0, 0>(int);
+template <> SolveKernelFn solve_kernel_table<0, 1>(int);
+template <> SolveKernelFn solve_kernel_table<1, 0>(int);
+template <> SolveKernelFn solve_kernel_table<1, 1>(int);
+template <> SolveKernelFn solve_kernel_table<2, 0>(int);
+template <> SolveKernelFn solve_kernel_table<2, 1>(int);
 
-SolveKernelFn solve_kernel_variant(int model, bool resto, int ig) {
-  if (resto) return ig ? solve_kernel_table<true, 1>(model) : solve_kernel_table<true, 0>(model);
-  return ig ? solve_kernel_table<false, 1>(model) : solve_kernel_table<false, 0>(model);
+SolveKernelFn solve_kernel_variant(int model, int resto, int ig) {
+  if (resto == 2) return ig ? solve_kernel_table<2, 1>(model) : solve_kernel_table<2, 0>(model);
+  if (resto == 1) return ig ? solve_kernel_table<1, 1>(model) : solve_kernel_table<1, 0>(model);
+  return ig ? solve_kernel_table<0, 1>(model) : solve_kernel_table<0, 0>(model);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -191,7 +194,7 @@ extern "C" int mpcr_create(const mpcr_config* cfg, mpcr_handle** out) {
     const char* e = getenv("MPCR_CARVEOUT");      // percent of the unified L1/shared array
     if (e && atoi(e) > 0 && atoi(e) <= 100) h->carve_env = atoi(e);
   }
-  const bool resto = h->cfg.o.restoration != 0;
+  const int resto = h->cfg.o.restoration;       // 0 off, 1 two-stage, 2 every problem in the restoration build
   const int ig = h->cfg.integrator;
   {
     mpcr_handle::Layout& L = h->warp;

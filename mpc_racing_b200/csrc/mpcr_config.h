@@ -133,7 +133,7 @@ inline bool config_valid(const mpcr_config& c, const char** why) {
   if (c.n_exp < 1.0) { *why = "n_exp must be >= 1"; return false; }
   if (c.solve_kernel < 0 || c.solve_kernel > 1) { *why = "unknown solve_kernel"; return false; }
   if (c.integrator < 0 || c.integrator > 1) { *why = "unknown integrator"; return false; }
-  if (c.restoration < 0 || c.restoration > 1) { *why = "restoration must be 0 or 1"; return false; }
+  if (c.restoration < 0 || c.restoration > 2) { *why = "restoration must be 0, 1 or 2"; return false; }
   if (c.schedule < 0 || c.schedule > 2) { *why = "unknown schedule"; return false; }
   if (!(c.polish_tol >= 0.0)) { *why = "polish_tol must be >= 0"; return false; }
   if (!(c.tol > 0.0) || !(c.acceptable_tol > 0.0)) { *why = "tol and acceptable_tol must be positive"; return false; }

@@ -322,6 +322,9 @@ struct WarpSolver {
   // the objective is wq/2 |d(x) - s|^2 + zeta/2 |D_R (x - x_R)|^2 and the rows' multipliers are o.resto_weight (d - s)
   bool resto_;
   MPCR_D bool in_resto() const { return RESTO && resto_; }
+  // plain build with mpcr_config.restoration set: the line search gave up where IPOPT would start
+  // its restoration phase - the caller re-solves this problem with the RESTO build (uniform)
+  bool wanted_resto;
   // packed slots of the stage-Hessian entries (r, lane), r = 0..11, one byte each (registers,
   // no runtime-indexed local array): rows 0-7 in colslot_lo, rows 8-11 in colslot_hi
   unsigned long long colslot_lo;
@@ -1366,6 +1369,7 @@ struct WarpSolver {
     fval = 0.0;
     barB = 0.0;
     resto_ = false;
+    wanted_resto = false;
     {
       int nr = 0, nb = 0;
 #pragma unroll 1
@@ -1678,6 +1682,7 @@ struct WarpSolver {
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
               if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              if (!RESTO && o.restoration && ls_fail_mode == 0) wanted_resto = true;
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
@@ -1796,6 +1801,7 @@ struct WarpSolver {
             phase = kPhBacktrack;
             if (!(alpha >= amin && n_ls < 60)) {
               if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              if (!RESTO && o.restoration && ls_fail_mode == 0) wanted_resto = true;
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
@@ -1833,6 +1839,7 @@ struct WarpSolver {
         phase = kPhBacktrack;
         if (!(alpha >= amin && n_ls < 60)) {
               if (RESTO && o.restoration && !resto_ && ls_fail_mode == 0) { want_resto = true; continue; }
+              if (!RESTO && o.restoration && ls_fail_mode == 0) wanted_resto = true;
               status = ls_fail_mode == 1 ? kSolvedToAcceptableLevel : kRestorationNeeded;
               break;
             }
@@ -1973,8 +1980,9 @@ MPCR_HD int lam_g_stride(const Config& c) {
   return 7 + c.N * (7 + (c.lane_con ? 1 : 0)) + 6 * c.N + 2;
 }
 
+// Returns true when the plain build gave up where the restoration phase would have started.
 template <int MODEL, bool RESTO = false, int IG = 0>
-MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
+MPCR_D bool solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& out, int b,
                           int trace_rows, double* wsbase) {
   const int N = cfg.N;
   ProblemView pv;
@@ -2032,6 +2040,16 @@ MPCR_D void solve_problem(const Config& cfg, const BatchIn& in, const BatchOut& 
   for (int k = lane_id(); k <= N; k += 32) solver.ws.st(k)[kOffZero] = 0.0;   // the always-zero slot of every stage record
   syncwarp();
   solver.solve(so);
+  return solver.wanted_resto;
+}
+
+// The restoration build as an out-of-line call (own register allocation; arguments by value so that
+// no address of a kernel parameter is taken on the hot path): problems that need the phase are
+// re-solved from the start with it.
+template <int MODEL, int IG>
+MPCR_NOINLINE void solve_problem_with_restoration(const Config* cfg, BatchIn in, BatchOut out, int b,
+                                                  int trace_rows, double* wsbase) {
+  solve_problem<MODEL, true, IG>(*cfg, in, out, b, trace_rows, wsbase);
 }
 
 // ---------------------------------------------------------------------------
@@ -2050,7 +2068,12 @@ struct WorkQueue {
   int B;
 };
 
-template <int MODEL, bool RESTO, int IG>
+// RMODE: 0 = no restoration phase; 1 = two-stage (mpcr_config.restoration = 1): every problem runs
+// the plain solver, the few that need the phase are solved again by the build that carries it;
+// 2 = every problem runs the restoration build (mpcr_config.restoration = 2: workloads in which many
+// problems need the phase, e.g. the lane rows - re-solving 5 % of a batch costs more than the 6 %
+// the phase's code costs everybody).
+template <int MODEL, int RMODE, int IG>
 MPCR_D void solve_batch(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
                         const WorkQueue& q, double* wsbase) {
   while (true) {
@@ -2061,25 +2084,40 @@ MPCR_D void solve_batch(const Config& cfg, const BatchIn& in, const BatchOut& ou
     }
     b = shfl_i(b, 0);
     if (b >= q.B) break;
-    solve_problem<MODEL, RESTO, IG>(cfg, in, out, b, trace_rows, wsbase);
-    syncwarp();
+    if (RMODE == 2) {
+      solve_problem<MODEL, true, IG>(cfg, in, out, b, trace_rows, wsbase);
+      syncwarp();
+    } else {
+      // two-stage: the hot path is the plain solver (no restoration code, registers or instruction-
+      // cache footprint); a problem whose line search gives up where IPOPT would restore is solved
+      // again, from the start, by the build that carries the phase - the result that build gives on
+      // its own, since it follows the same path up to there.
+      const bool again = solve_problem<MODEL, false, IG>(cfg, in, out, b, trace_rows, wsbase);
+      syncwarp();
+      if (RMODE == 1 && again) {
+        solve_problem_with_restoration<MODEL, IG>(&cfg, in, out, b, trace_rows, wsbase);
+        syncwarp();
+      }
+    }
   }
 }
 
-template <bool RESTO, int IG>
+template <int RMODE, int IG>
 MPCR_D void solve_batch_model(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
                               const WorkQueue& q, double* wsbase) {
-  if (cfg.model == kDynamic) solve_batch<kDynamic, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
-  else if (cfg.model == kKinematic) solve_batch<kKinematic, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
-  else solve_batch<kBlended, RESTO, IG>(cfg, in, out, trace_rows, q, wsbase);
+  if (cfg.model == kDynamic) solve_batch<kDynamic, RMODE, IG>(cfg, in, out, trace_rows, q, wsbase);
+  else if (cfg.model == kKinematic) solve_batch<kKinematic, RMODE, IG>(cfg, in, out, trace_rows, q, wsbase);
+  else solve_batch<kBlended, RMODE, IG>(cfg, in, out, trace_rows, q, wsbase);
 }
 
 // host builds (tests/emu): runtime dispatch over every instantiation
 MPCR_D void solve_batch_any(const Config& cfg, const BatchIn& in, const BatchOut& out, int trace_rows,
                             const WorkQueue& q, double* wsbase) {
-  const bool rs = cfg.o.restoration != 0, ig = cfg.integrator != 0;
-  if (rs) { if (ig) solve_batch_model<true, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<true, 0>(cfg, in, out, trace_rows, q, wsbase); }
-  else { if (ig) solve_batch_model<false, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<false, 0>(cfg, in, out, trace_rows, q, wsbase); }
+  const int rs = cfg.o.restoration;
+  const bool ig = cfg.integrator != 0;
+  if (rs == 2) { if (ig) solve_batch_model<2, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<2, 0>(cfg, in, out, trace_rows, q, wsbase); }
+  else if (rs == 1) { if (ig) solve_batch_model<1, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<1, 0>(cfg, in, out, trace_rows, q, wsbase); }
+  else { if (ig) solve_batch_model<0, 1>(cfg, in, out, trace_rows, q, wsbase); else solve_batch_model<0, 0>(cfg, in, out, trace_rows, q, wsbase); }
 }
 
 }  // namespace mpcr

@@ -8,21 +8,21 @@ namespace mpcr {
 
 typedef void (*SolveKernelFn)(const Config, const BatchIn, const BatchOut, int, int, int*, const int*);
 
-// kernel for (model, restoration, integrator); defined in mpcr.cu over the per-variant tables
-SolveKernelFn solve_kernel_variant(int model, bool resto, int ig);
+// kernel for (model, restoration mode 0 / 1 / 2, integrator); defined in mpcr.cu over the per-variant tables
+SolveKernelFn solve_kernel_variant(int model, int resto, int ig);
 
 #if defined(__CUDACC__)
 // Persistent: block = one warp that pulls problems off the batch's work queue until it runs dry.
-template <int MODEL, bool RESTO, int IG>
+template <int MODEL, int RMODE, int IG>
 __global__ void __launch_bounds__(32, 1)
 solve_kernel(const __grid_constant__ Config cfg, const BatchIn in, const BatchOut out, int B,
              int trace_rows, int* __restrict__ counter, const int* __restrict__ order) {
   extern __shared__ __align__(16) double smem[];
   WorkQueue q{counter, order, B};
-  solve_batch<MODEL, RESTO, IG>(cfg, in, out, trace_rows, q, smem);
+  solve_batch<MODEL, RMODE, IG>(cfg, in, out, trace_rows, q, smem);
 }
 
-template <bool RESTO, int IG>
+template <int RMODE, int IG>
 SolveKernelFn solve_kernel_table(int model);      // one explicit specialisation per translation unit
 #endif
 

@@ -5,14 +5,14 @@
 #include "mpcr_solve_kernel.cuh"
 
 #if !defined(MPCR_V_RESTO) || !defined(MPCR_V_IG)
-#error "build with -DMPCR_V_RESTO=0|1 -DMPCR_V_IG=0|1"
+#error "build with -DMPCR_V_RESTO=0|1|2 -DMPCR_V_IG=0|1"
 #endif
 
 namespace mpcr {
 
 template <>
-SolveKernelFn solve_kernel_table<(MPCR_V_RESTO != 0), MPCR_V_IG>(int model) {
-  constexpr bool R = MPCR_V_RESTO != 0;
+SolveKernelFn solve_kernel_table<MPCR_V_RESTO, MPCR_V_IG>(int model) {
+  constexpr int R = MPCR_V_RESTO;
   constexpr int I = MPCR_V_IG;
   if (model == kDynamic) return solve_kernel<kDynamic, R, I>;
 #if !defined(MPCR_ONLY_DYNAMIC)      // development builds: one model, a third of the compile time

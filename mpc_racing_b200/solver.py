@@ -80,7 +80,12 @@ class BatchedMPC:
         cfg.solve_kernel = int({"auto": 0, "warp": 1}.get(solve_kernel, solve_kernel))
         # "euler" = the reference's discretisation; "rk4" = extension (same kernel, 32-entry stage Jacobian)
         cfg.integrator = int({"euler": 0, "rk4": 1}.get(integrator, integrator))
-        cfg.restoration = int(bool(restoration))     # feasibility restoration phase; off = status -2 instead
+        # feasibility restoration phase (off = status -2 instead).  True picks the launch mode: two-stage
+        # (plain solver + re-solve of the few problems that need the phase) unless the lane rows are on,
+        # where ~5 % of the problems need it and the build with the phase for everybody is cheaper;
+        # "two-stage" / "always" (or 1 / 2) force a mode
+        mode = {False: 0, True: (2 if lane_constraint else 1), "two-stage": 1, "always": 2}.get(restoration, restoration)
+        cfg.restoration = int(mode)
         # dispatch order of the batch: "auto" = expected-longest-first for batches above one wave
         cfg.schedule = int({"auto": 0, "index": 1, "curvature": 2}.get(schedule, schedule))
         # > 0: keep iterating to this tolerance after the first termination (status / iters report the first)

@@ -264,4 +264,12 @@ def test_restoration_phase_on_gpu():
     # a rescued problem against the independent optimum (scipy trust-constr) of the oracle study
     b = 478
     assert plain.status[b] == -2 and g['status'][b] == -2 and resc.status[b] == 0
+    # the two launch modes of the phase - every problem in the build that carries it ("always", what
+    # restoration=True picks with lane rows) against the two-stage mode (plain solver + re-solve of
+    # the problems that need the phase) - return the same solutions
+    two = BatchedMPC(N=30, Ts=0.05, lane_constraint=True, restoration="two-stage").solve(*args, max_err=d['max_err'])
+    assert np.array_equal(two.status >= 0, resc.status >= 0)
+    same2 = two.iters == resc.iters
+    assert same2.mean() >= 0.97
+    assert np.abs(two.obj[same2] - resc.obj[same2]).max() <= 1e-9 * np.abs(resc.obj).max()
     assert abs(resc.obj[b] - (-112828.3055199883)) <= 1e-6 * 112828.3
