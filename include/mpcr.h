@@ -162,6 +162,13 @@ int mpcr_solve_batch_trace(mpcr_handle* h, int B, const double* x0, const double
                            double* lam_g, double* obj, int32_t* status, int32_t* iters,
                            double* trace, void* cuda_stream);
 
+/* Expected-cost keys for the dispatch order of the NEXT solves of this handle (any schedule that
+ * reorders): keys [B] int32 on the device, e.g. the iteration counts the same problems took in the
+ * previous control step of a closed loop; larger = dispatched earlier.  NULL = back to the built-in
+ * key (curvature of the reference path).  The array is read when a solve is launched; it must stay
+ * valid until then.  Only the order of the work changes, never a result. */
+int mpcr_set_dispatch_keys(mpcr_handle* h, const int32_t* keys);
+
 /* Device time of the last solve in milliseconds: the solve kernel and, when the batch was
  * reordered (mpcr_config.schedule), the two schedule kernels before it (CUDA events on the
  * launch stream); blocks until that launch has finished. */

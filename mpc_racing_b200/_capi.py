@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "mpcr_launch_info", "mpcr_last_launch_count", "mpcr_fp64_peak_tflops",
     "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
     "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step", "mpcr_model_eval",
-    "mpcr_rollout_prepare", "mpcr_rollout_apply",
+    "mpcr_rollout_prepare", "mpcr_rollout_apply", "mpcr_set_dispatch_keys",
 ]
 
 
@@ -123,6 +123,8 @@ def load_library(path=None):
     lib.mpcr_plant_step.restype = C.c_int
     lib.mpcr_model_eval.argtypes = [V, C.c_int, C.c_int, C.c_int, V, V, C.c_double, V, V, V, V, V]
     lib.mpcr_model_eval.restype = C.c_int
+    lib.mpcr_set_dispatch_keys.argtypes = [V, V]
+    lib.mpcr_set_dispatch_keys.restype = C.c_int
     lib.mpcr_rollout_prepare.argtypes = [V, C.POINTER(MpcrRolloutBufs), V]
     lib.mpcr_rollout_prepare.restype = C.c_int
     lib.mpcr_rollout_apply.argtypes = [V, C.POINTER(MpcrRolloutBufs), V, V, V]

@@ -51,9 +51,20 @@ constexpr int kSchedBins = 256;
 
 __global__ void __launch_bounds__(256)
 schedule_bin_kernel(const BatchIn in, int B, int N, double Ts, int* __restrict__ hist,
-                    unsigned char* __restrict__ bin) {
+                    unsigned char* __restrict__ bin, const int32_t* __restrict__ keys) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (keys) {
+    // caller-supplied expected cost (closed loop: the iteration count of the same vehicle's previous
+    // solve): largest first, one bin per unit up to 255
+    int kq = keys[b];
+    if (kq < 0) kq = 0;
+    if (kq > kSchedBins - 1) kq = kSchedBins - 1;
+    const int qk = (kSchedBins - 1) - kq;
+    bin[b] = (unsigned char)qk;
+    atomicAdd(&hist[qk], 1);
+    return;
+  }
   const double* cx = in.cx + (size_t)5 * b;
   const double* cy = in.cy + (size_t)5 * b;
   const double s0 = in.s0[b];
@@ -136,6 +147,7 @@ struct mpcr_handle {
   bool launched = false;
   int last_blocks = 0, last_smem = 0;    // geometry of the last launch
   int schedule = MPCR_SCHEDULE_AUTO;     // config / MPCR_SCHEDULE env
+  const int32_t* dispatch_keys = nullptr; // mpcr_set_dispatch_keys: device array [B] or null (= curvature key)
   int* d_order = nullptr;                // dispatch order [order_cap] | histogram + cursors [2 * 256]
   unsigned char* d_bin = nullptr;
   int order_cap = 0;
@@ -233,6 +245,16 @@ extern "C" int mpcr_destroy(mpcr_handle* h) {
   return MPCR_OK;
 }
 
+extern "C" int mpcr_set_dispatch_keys(mpcr_handle* h, const int32_t* keys) {
+  if (!h) return MPCR_ERR_INVALID_ARG;
+  if (keys && !h->pub.pointers_on_device) {
+    h->err = "mpcr_set_dispatch_keys: device pointer, handle with pointers_on_device = 1";
+    return MPCR_ERR_INVALID_ARG;
+  }
+  h->dispatch_keys = keys;
+  return MPCR_OK;
+}
+
 extern "C" int mpcr_lam_g_stride(mpcr_handle* h) {
   if (!h) return MPCR_ERR_INVALID_ARG;
   return lam_g_stride(h->cfg);
@@ -311,7 +333,7 @@ static int launch_solve(mpcr_handle* h, int B, const BatchIn& in, const BatchOut
     int* hist = h->d_order + h->order_cap;
     CK(cudaMemsetAsync(hist, 0, 2 * kSchedBins * sizeof(int), st));
     const int nb = (B + 255) / 256;
-    schedule_bin_kernel<<<nb, 256, 0, st>>>(in, B, h->cfg.N, h->cfg.Ts, hist, h->d_bin);
+    schedule_bin_kernel<<<nb, 256, 0, st>>>(in, B, h->cfg.N, h->cfg.Ts, hist, h->d_bin, h->dispatch_keys);
     schedule_scatter_kernel<<<nb, 256, 0, st>>>(B, hist, hist + kSchedBins, h->d_bin, h->d_order);
     CK(cudaGetLastError());
     order = h->d_order;

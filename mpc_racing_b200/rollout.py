@@ -46,6 +46,7 @@ class ClosedLoopRollouts:
         self.estimate_state = bool(estimate_state)       # agent.py:240-254 instead of the true plant state
         self.start_control_at = int(start_control_at)    # agent.py:66 (the agent waits 50 ticks)
         self.use_graph = bool(use_graph)
+        self.keyed_dispatch = True
         # closed loop: every solve runs the build with the restoration phase ("always").  The two-stage
         # mode re-solves the problems that need the phase; in a warm-started loop a step takes ~1 ms per
         # problem and a re-solve 10-20 ms, which becomes the tail of every step (measured: 26.5 -> 32.0 ms).
@@ -119,6 +120,8 @@ class ClosedLoopRollouts:
         cur, prev = S.plan[k % 2], S.plan[(k + 1) % 2]
         if k >= self.start_control_at:
             warm = prev["U"] if k > self.start_control_at else None      # agent.py:205: last_controls
+            # dispatch the vehicles whose previous solve took longest first
+            self.solver.set_dispatch_keys(prev["iters"] if (warm is not None and self.keyed_dispatch) else None)
             self.solver.solve(S.x_mpc, S.u_prev, S.progress, S.cx, S.cy, params=S.params, u_warm=warm,
                               want_lam_g=False, out=cur, stream=st)
         self._chk(self.lib.mpcr_rollout_apply(self.solver._h, C.byref(S.bufs), cur["U"].data_ptr(),

@@ -127,6 +127,10 @@ class BatchedMPC:
         self._check(self.lib.mpcr_fp64_peak_tflops(self._h, C.byref(v)))
         return v.value
 
+    def set_dispatch_keys(self, keys):
+        """Expected-cost keys (int32 CUDA tensor [B] or None) for the dispatch order of the next solves."""
+        self._check(self.lib.mpcr_set_dispatch_keys(self._h, None if keys is None else keys.data_ptr()))
+
     def last_kernel_ms(self):
         ms = C.c_float()
         rc = self.lib.mpcr_last_kernel_ms(self._h, C.byref(ms))

@@ -71,3 +71,23 @@ def test_one_handle_from_two_streams_is_serialised_on_the_device():
     for oa, ob in outs:
         assert torch.equal(oa.U, ra) and torch.equal(ob.U, rb)
         assert torch.equal(oa.iters, ref_a.iters) and torch.equal(ob.status, ref_b.status)
+
+
+def test_dispatch_keys_change_the_order_not_the_results():
+    """mpcr_set_dispatch_keys (closed loop: the previous step's iteration counts): any key array gives
+    the results of the index-order run, bit for bit."""
+    import torch
+    from mpc_racing_b200.solver import BatchedMPC
+    d = make_batch(3000)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    A = [t(d[k]) for k in ("x0", "u_prev", "s0", "cx", "cy")]
+    ref = BatchedMPC(N=30, Ts=0.05, on_device=True, schedule="index").solve(*A)
+    s = BatchedMPC(N=30, Ts=0.05, on_device=True, schedule="curvature")
+    rng = np.random.default_rng(0)
+    for keys in (ref.iters.clone(), torch.from_numpy(rng.integers(-5, 400, 3000).astype(np.int32)).to(dev), None):
+        s.set_dispatch_keys(keys)
+        r = s.solve(*A)
+        torch.cuda.synchronize()
+        for k in ("U", "X", "S", "lam_g", "obj", "status", "iters"):
+            assert torch.equal(getattr(r, k), getattr(ref, k)), k

@@ -2,7 +2,7 @@
 warm-started) and where a control step's time goes: per-kernel CUDA-event times of ungraphed ticks,
 then the graphed engine's steps per second.
 
-    python tools/rollout_rate.py [R] [K] [track] [warp|auto]
+    python tools/rollout_rate.py [R] [K] [track] [warp|auto] [keyed dispatch 0|1]
 """
 import ctypes as C
 import sys, os, time
@@ -16,8 +16,10 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 track = sys.argv[3] if len(sys.argv) > 3 else "t4"
 layout = sys.argv[4] if len(sys.argv) > 4 else "auto"
+keyed = bool(int(sys.argv[5])) if len(sys.argv) > 5 else True
 cl = ParameterizedCenterline(track, lanes=False, error=False)
 ro = ClosedLoopRollouts(cl, N=15, Ts=0.05, plant="blended", restoration=True, solve_kernel=layout)
+ro.keyed_dispatch = keyed
 x0, s0 = start_states(cl, R, seed=1234, v0=5.0)
 S = ro.begin(x0, s0)
 ro.advance(S, 6)                                   # warm-up (allocations, first-launch costs, graph capture)
@@ -41,7 +43,7 @@ with torch.cuda.stream(ro.stream):
         S.k += 1
         ro.stream.synchronize()
         tp.append(e[0].elapsed_time(e[1])); ts.append(e[1].elapsed_time(e[2])); ta.append(e[2].elapsed_time(e[3]))
-print(f"{track} R={R} layout={layout}: prepare {np.median(tp):.3f} ms, solve {np.median(ts):.3f} ms "
+print(f"{track} R={R} layout={layout} keyed_dispatch={keyed}: prepare {np.median(tp):.3f} ms, solve {np.median(ts):.3f} ms "
       f"(kernel {ro.solver.last_kernel_ms():.3f}), apply {np.median(ta):.3f} ms; launch {ro.solver.launch_info()}")
 if S.k % 2:
     ro.advance(S, 1)
