@@ -595,7 +595,8 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
     total_ms = e0.elapsed_time(e1)
     _barrier(torch, dist, world, dev)
     solve_ms = float(np.mean([e["ro"].solver.last_kernel_ms() for e in engines]))
-    launches = sum(e["ro"].launches_per_step for e in engines) * K * args.steps
+    # kernels of this library per control step: prepare + apply + the solve's 1 (or 3 with the dispatch order)
+    launches = sum(2 + max(1, e["ro"].solver.launch_info()["kernels_per_solve"]) for e in engines) * K * args.steps
     # ---- e2e: the public API with host arrays in and out every step
     _barrier(torch, dist, world, dev)
     t0 = time.perf_counter()

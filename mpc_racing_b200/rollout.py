@@ -56,7 +56,6 @@ class ClosedLoopRollouts:
         self.lib = self.solver.lib
         self.track = centerline.device_track(self.solver)
         self.stream = torch.cuda.Stream(device=self.dev)
-        self.launches_per_step = 5       # prepare, 2 schedule kernels (large batches), solve, apply
 
     def close(self):
         if self.track:
