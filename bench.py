@@ -447,7 +447,7 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     per_rank = rank_stats([float(np.mean(kern_ms)), float(np.mean(step_ms)), e2e_s * 1e3 / args.steps, plain_ms,
-                           float(B)], world, dist, dev)
+                           float(B), float(iters.sum())], world, dist, dev)
     total_ms_max, e2e_ms_max = t.tolist()
     conv_all, e2e_conv_all, _, b_all, plain_conv_all = c.tolist()
     if rank != 0:
@@ -485,7 +485,9 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         except Exception as exc:
             cpu["numpy_port_value"] = None
             cpu["numpy_port_sample"] = repr(exc)[:120]
-    names = ["kernel_ms", "step_ms", "e2e_step_ms", "kernel_ms_no_restoration", "problems"]
+    # ipm_iterations: the work of a rank's slice - a rank whose kernel takes longer because its problems
+    # need more iterations is not a straggler
+    names = ["kernel_ms", "step_ms", "e2e_step_ms", "kernel_ms_no_restoration", "problems", "ipm_iterations"]
     ranks = {n: {"min": float(per_rank[:, i].min()), "median": float(np.median(per_rank[:, i])),
                  "max": float(per_rank[:, i].max()), "per_rank": [float(v) for v in per_rank[:, i]]}
              for i, n in enumerate(names)}
