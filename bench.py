@@ -82,7 +82,7 @@ def clocks_sampler(stop, samples, gpu_index):
                 samples.append([x.strip() for x in out.split(",")])
         except Exception:
             pass
-        stop.wait(0.5)
+        stop.wait(0.25)
 
 
 def summarize_clocks(samples):
