@@ -437,6 +437,32 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         ts = np.array(ts[10:]) * 1e3
         lat = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)),
                "batch": 1, "calls": int(ts.size), "includes": "H2D + solve kernel + D2H, host pointers"}
+    # ---- the production use (agent.py:138-205): ONE vehicle in closed loop, N = 15, warm-started from
+    #      the previous plan; a tick = prepare (projection + refit) + solve + plant step, host-synchronised
+    tick = None
+    if rank == 0 and not cfg["lane"]:
+        try:
+            from mpc_racing_b200.rollout import ClosedLoopRollouts, start_states
+            from mpc_racing_b200.splines.ParameterizedCenterline import ParameterizedCenterline
+            cl = ParameterizedCenterline("t4", lanes=False, error=False, device=local)
+            ro = ClosedLoopRollouts(cl, N=15, Ts=TS, plant="blended", device=local, restoration=True, use_graph=False)
+            x1, s1 = start_states(cl, 1, seed=4321, v0=10.0)
+            S1 = ro.begin(x1, s1)
+            tt = []
+            for i in range(120):
+                t1 = time.perf_counter()
+                with torch.cuda.stream(ro.stream):
+                    ro._tick(S1, S1.k, ro.stream)
+                    S1.k += 1
+                ro.stream.synchronize()
+                tt.append(time.perf_counter() - t1)
+            tt = np.array(tt[20:]) * 1e3
+            tick = {"p50_ms": float(np.percentile(tt, 50)), "p90_ms": float(np.percentile(tt, 90)), "ticks": int(tt.size),
+                    "what": "one vehicle on t4, N = 15, blended plant, warm-started: prepare + solve + apply, "
+                            "synchronised every tick (the reference agent's per-tick MPC time, agent.py:170-185)"}
+            ro.close()
+        except Exception as exc:           # the closed-loop probe is context, never a reason to lose the line
+            tick = {"unavailable": repr(exc)[:200]}
     h2d = sum(pin[k].nbytes for k in pin)
     d2h = sum(v.nbytes for v in hout.values() if v is not None)
     stop.set()
@@ -518,6 +544,7 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         "ranks": ranks,
         "cpu_baseline": cpu,
         "single_solve_latency": lat,
+        "closed_loop_tick_latency": tick,
     }
     print(json.dumps(line), flush=True)
 

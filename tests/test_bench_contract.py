@@ -27,3 +27,27 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ["cfg2", "cfg4"])
+def test_gpu_arm_json_line(config):
+    """The GPU arm prints one JSON line with the keys of the bench contract (small batch, no CPU leg)."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", config, "--steps", "2", "--warmup", "1",
+           "--batch", "2048", "--inner", "4", "--no-cpu-baseline"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert line["metric"] == "converged_nmpc_solves_per_sec" and line["unit"] == "solves/s" and line["value"] > 0
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1 and line["dtype"] == "f64"
+    assert line["config"]["name"] == config and line["config"]["restoration"] is True
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["gpu_launches"] >= 2 and "sm_mhz" in line["clocks"] and "roofline" in line and "ranks" in line
+    if config == "cfg2":
+        r = line["roofline"]
+        assert r["bound"] == "fp64" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        assert line["no_restoration"]["value"] > 0 and line["single_solve_latency"]["p50_ms"] > 0
+        assert line["closed_loop_tick_latency"]["p50_ms"] > 0
