@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MPCR_VERSION 104
+#define MPCR_VERSION 105
 
 /* models (control/MPC.py:186 f_vehicle = dynamic, :231 f_vehicle_kinematic,
  * models/BlendedBicycleModel.py:23-46 blend of the two) */
@@ -152,6 +152,21 @@ int mpcr_solve_batch(mpcr_handle* h, int B,
                      int32_t* status       /* [B] */,
                      int32_t* iters        /* [B] */,
                      void* cuda_stream     /* cudaStream_t or NULL */);
+
+/* Same call, but with HOST pointers it returns as soon as the copies and the kernels are enqueued on
+ * `cuda_stream`: the inputs must stay valid and the outputs are undefined until the caller has
+ * synchronised that stream (use page-locked host memory, or the copies are not asynchronous).  With
+ * device pointers it is identical to mpcr_solve_batch (always asynchronous).  Two handles on two
+ * streams used alternately form a pipeline: the copies of one batch and the tail of its launch (the
+ * last long problems of the persistent kernel) overlap the head of the next batch
+ * (mpc_racing_b200/pipeline.py).  The reference has no counterpart (control/MPC.py:152-181 solves
+ * one problem per call, blocking). */
+int mpcr_solve_batch_async(mpcr_handle* h, int B, const double* x0, const double* u_prev,
+                           const double* s0, const double* cx, const double* cy,
+                           const double* max_err, const double* params, const double* u_warm,
+                           double* U, double* X, double* S, double* eC, double* eL,
+                           double* lam_g, double* obj, int32_t* status, int32_t* iters,
+                           void* cuda_stream);
 
 /* Debug variant: also writes the per-iteration trace [B, max_iter+1, 8]
  * (obj, E0, pr_inf, dual_inf, compl, mu, alpha, delta_w). */

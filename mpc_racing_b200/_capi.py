@@ -43,7 +43,7 @@ SOLVE_ARGTYPES = [C.c_void_p] * 8 + [C.c_void_p] * 9   # 8 inputs, 9 outputs (ra
 # every symbol include/mpcr.h declares
 EXPORTED_SYMBOLS = [
     "mpcr_version", "mpcr_config_default", "mpcr_create", "mpcr_destroy", "mpcr_last_error",
-    "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
+    "mpcr_lam_g_stride", "mpcr_solve_batch", "mpcr_solve_batch_async", "mpcr_solve_batch_trace", "mpcr_last_kernel_ms",
     "mpcr_launch_info", "mpcr_last_launch_count", "mpcr_fp64_peak_tflops",
     "mpcr_track_create", "mpcr_track_destroy", "mpcr_track_eval", "mpcr_track_coeffs",
     "mpcr_track_project", "mpcr_track_lookup_error", "mpcr_plant_step", "mpcr_model_eval",
@@ -96,6 +96,8 @@ def load_library(path=None):
     lib.mpcr_lam_g_stride.restype = C.c_int
     lib.mpcr_solve_batch.argtypes = [C.c_void_p, C.c_int] + SOLVE_ARGTYPES + [C.c_void_p]
     lib.mpcr_solve_batch.restype = C.c_int
+    lib.mpcr_solve_batch_async.argtypes = [C.c_void_p, C.c_int] + SOLVE_ARGTYPES + [C.c_void_p]
+    lib.mpcr_solve_batch_async.restype = C.c_int
     lib.mpcr_solve_batch_trace.argtypes = [C.c_void_p, C.c_int] + SOLVE_ARGTYPES + [C.c_void_p, C.c_void_p]
     lib.mpcr_solve_batch_trace.restype = C.c_int
     lib.mpcr_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]

@@ -354,7 +354,7 @@ static int solve_impl(mpcr_handle* h, int B, const double* x0, const double* u_p
                       const double* s0, const double* cx, const double* cy, const double* max_err,
                       const double* params, const double* u_warm, double* U, double* X, double* S,
                       double* eC, double* eL, double* lam_g, double* obj, int32_t* status,
-                      int32_t* iters, double* trace, void* stream) {
+                      int32_t* iters, double* trace, void* stream, bool sync = true) {
   if (!h) return MPCR_ERR_INVALID_ARG;
   if (B < 0 || !x0 || !u_prev || !s0 || !cx || !cy || !U || !X || !S || !eC || !eL || !obj ||
       !status || !iters) {
@@ -443,7 +443,14 @@ static int solve_impl(mpcr_handle* h, int B, const double* x0, const double* u_p
   if (trace) CK(d2h(trace, d_tr, ntr));
   CK(cudaMemcpyAsync(status, d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(iters, d_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  {
+    // the staging buffers are in use until the copies above are done: the next solve on this handle
+    // (any stream) is ordered behind them
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cap));
+    if (cap == cudaStreamCaptureStatusNone) CK(cudaEventRecord(h->ev_done, st));
+  }
+  if (sync) CK(cudaStreamSynchronize(st));
   return MPCR_OK;
 }
 
@@ -455,6 +462,16 @@ extern "C" int mpcr_solve_batch(mpcr_handle* h, int B, const double* x0, const d
                                 void* cuda_stream) {
   return solve_impl(h, B, x0, u_prev, s0, cx, cy, max_err, params, u_warm, U, X, S, eC, eL, lam_g,
                     obj, status, iters, nullptr, cuda_stream);
+}
+
+extern "C" int mpcr_solve_batch_async(mpcr_handle* h, int B, const double* x0, const double* u_prev,
+                                      const double* s0, const double* cx, const double* cy,
+                                      const double* max_err, const double* params, const double* u_warm,
+                                      double* U, double* X, double* S, double* eC, double* eL,
+                                      double* lam_g, double* obj, int32_t* status, int32_t* iters,
+                                      void* cuda_stream) {
+  return solve_impl(h, B, x0, u_prev, s0, cx, cy, max_err, params, u_warm, U, X, S, eC, eL, lam_g,
+                    obj, status, iters, nullptr, cuda_stream, false);
 }
 
 extern "C" int mpcr_solve_batch_trace(mpcr_handle* h, int B, const double* x0,

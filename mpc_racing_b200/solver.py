@@ -162,22 +162,27 @@ class BatchedMPC:
 
     # ------------------------------------------------------------------
     def solve(self, x0, u_prev, s0, cx, cy, max_err=None, params=None, u_warm=None,
-              want_lam_g=True, trace=False, stream=None, out=None) -> BatchResult:
+              want_lam_g=True, trace=False, stream=None, out=None, sync=True) -> BatchResult:
+        """``sync=False`` (host arrays only; device mode is always asynchronous): return once the
+        copies and kernels are enqueued on ``stream`` (mpcr_solve_batch_async) - the inputs must
+        stay untouched and the outputs are undefined until that stream is synchronised."""
         if self.on_device:
             return self._solve_device(x0, u_prev, s0, cx, cy, max_err, params, u_warm,
                                       want_lam_g, trace, stream, out)
         return self._solve_host(x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g,
-                                trace, stream, out)
+                                trace, stream, out, sync)
 
     def _check(self, rc):
         if rc != 0:
             raise _capi.MpcrError(f"mpcr_solve_batch failed (rc={rc}): "
                                   f"{self.lib.mpcr_last_error(self._h).decode()}")
 
-    def _call(self, B, ins, outs, trace_ptr, stream):
+    def _call(self, B, ins, outs, trace_ptr, stream, sync=True):
         args = [self._h, int(B)] + ins + outs
         if trace_ptr is not None:
             self._check(self.lib.mpcr_solve_batch_trace(*args, trace_ptr, stream))
+        elif not sync:
+            self._check(self.lib.mpcr_solve_batch_async(*args, stream))
         else:
             self._check(self.lib.mpcr_solve_batch(*args, stream))
 
@@ -200,7 +205,7 @@ class BatchedMPC:
         return o
 
     def _solve_host(self, x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g, trace,
-                    stream, out):
+                    stream, out, sync=True):
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         x0, u_prev, s0, cx, cy, max_err, params, u_warm = map(
             f, (x0, u_prev, s0, cx, cy, max_err, params, u_warm))
@@ -215,8 +220,11 @@ class BatchedMPC:
         tr = np.zeros((B, self.cfg.max_iter + 1, 8)) if trace else None
         self._call(B, [ptr(a) for a in (x0, u_prev, s0, cx, cy, max_err, params, u_warm)],
                    [ptr(o[k]) for k in ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters")],
-                   ptr(tr) if trace else None, stream)
-        return BatchResult(trace=tr, **o)
+                   ptr(tr) if trace else None, stream, sync)
+        res = BatchResult(trace=tr, **o)
+        if not sync:
+            res._keepalive = (x0, u_prev, s0, cx, cy, max_err, params, u_warm)   # read by the copies later
+        return res
 
     def _solve_device(self, x0, u_prev, s0, cx, cy, max_err, params, u_warm, want_lam_g, trace,
                       stream, out):

@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_version_and_default_config(lib):
-    assert lib.mpcr_version() == 104
+    assert lib.mpcr_version() == 105
     cfg = _capi.MpcrConfig()
     lib.mpcr_config_default.argtypes = [ctypes.POINTER(_capi.MpcrConfig)]
     lib.mpcr_config_default(ctypes.byref(cfg))

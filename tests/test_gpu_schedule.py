@@ -91,3 +91,45 @@ def test_dispatch_keys_change_the_order_not_the_results():
         torch.cuda.synchronize()
         for k in ("U", "X", "S", "lam_g", "obj", "status", "iters"):
             assert torch.equal(getattr(r, k), getattr(ref, k)), k
+
+
+def test_pipelined_batches_are_bit_identical_to_serial_solves():
+    """mpc_racing_b200/pipeline.py: two handles on two streams, batches enqueued back to back
+    (mpcr_solve_batch_async with host arrays) - overlapping launches change nothing in the results."""
+    import torch
+    from mpc_racing_b200.pipeline import SolvePipeline
+    from mpc_racing_b200.solver import BatchedMPC
+    b = make_batch(4 * 1500)
+    keys = ("x0", "u_prev", "s0", "cx", "cy")
+    parts = [{k: np.ascontiguousarray(b[k][i * 1500:(i + 1) * 1500]) for k in keys} for i in range(4)]
+    serial = BatchedMPC(N=30, Ts=0.05, restoration=True)
+    ref = [serial.solve(*[p[k] for k in keys]) for p in parts]
+    names = ("U", "X", "S", "eC", "eL", "lam_g", "obj", "status", "iters")
+    # host arrays (page-locked), results copied out before the slot is reused
+    pipe = SolvePipeline(depth=2, host=True, N=30, Ts=0.05, restoration=True)
+    pinned = [{k: torch.from_numpy(p[k]).pin_memory().numpy() for k in keys} for p in parts]
+    got = {}
+    tickets = []
+    for i, p in enumerate(pinned):
+        tickets.append(pipe.submit(*[p[k] for k in keys]))
+        if i >= 1:                                     # consume the previous batch while this one runs
+            r = pipe.result(tickets[i - 1])
+            got[i - 1] = {k: np.array(getattr(r, k)) for k in names}
+    r = pipe.result(tickets[-1])
+    got[3] = {k: np.array(getattr(r, k)) for k in names}
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])                        # its slot has been reused
+    pipe.close()
+    for i in range(4):
+        for k in names:
+            assert np.array_equal(got[i][k], getattr(ref[i], k), equal_nan=True), (i, k)
+    # device arrays
+    dpipe = SolvePipeline(depth=2, host=False, N=30, Ts=0.05, restoration=True)
+    dev = [{k: torch.from_numpy(p[k]).cuda() for k in keys} for p in parts]
+    for i in (0, 1):
+        dpipe.submit(*[dev[i][k] for k in keys])
+    for i in (0, 1):
+        r = dpipe.result(i)
+        for k in names:
+            assert np.array_equal(getattr(r, k).cpu().numpy(), getattr(ref[i], k), equal_nan=True), (i, k)
+    dpipe.close()
