@@ -51,3 +51,6 @@ def test_gpu_arm_json_line(config):
         assert r["bound"] == "fp64" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
         assert line["no_restoration"]["value"] > 0 and line["single_solve_latency"]["p50_ms"] > 0
         assert line["closed_loop_tick_latency"]["p50_ms"] > 0
+        # value / e2e go through the two-deep pipeline; the one-launch-at-a-time figure sits beside them
+        assert line["serial"]["value"] > 0 and line["detail"]["pipeline_results_bit_identical_to_serial"] is True
+        assert line["value"] > 0.9 * line["serial"]["value"]
