@@ -237,7 +237,7 @@ class CpuClosedLoop:
         return conv
 
 
-def rollout_starts(cfg, R, rank=0, world=1):
+def rollout_starts(cfg, R, rank=0, world=1, split=1):
     """Start states of config 4 / 5: per track, s0 ~ U[0, L) on the centerline, tangent yaw, v0 = 5."""
     from mpc_racing_b200.sharding import shard_range
     tracks = cfg["tracks"]
@@ -256,7 +256,13 @@ def rollout_starts(cfg, R, rank=0, world=1):
         return out, len(pairs)
     per = R // len(tracks)
     for j, t in enumerate(tracks):
-        out.append((t, per if j < len(tracks) - 1 else R - per * (len(tracks) - 1), None, 1234 + 17 * rank + j))
+        n = per if j < len(tracks) - 1 else R - per * (len(tracks) - 1)
+        # `split` engines per track: sub-fleets on their own streams, so that the tail of one engine's
+        # solve launch is filled by the others (same idea as the solve pipeline; the fleets are independent)
+        for q in range(split):
+            lo, hi = shard_range(n, q, split)
+            if hi > lo:
+                out.append((t, hi - lo, None, 1234 + 17 * rank + j + 1000 * q))
     return out, R
 
 
@@ -423,16 +429,16 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
     iters = res.iters.cpu().numpy()
     conv_local = int((status >= 0).sum())
     launch = dsolver.launch_info()
-    # ---- timed region of the headline: the same K steps through the two-deep pipeline
+    # ---- timed region of the headline: the same K steps through the solve pipeline (--pipeline-depth, default 3)
     #      (mpc_racing_b200/pipeline.py): step i+1 is enqueued on a second handle / stream while step i
     #      runs, so the tail of one persistent launch (its last long problems) is filled by the next
     #      batch.  Inputs resident in HBM; the L2 flush precedes every step on that step's stream.
     from mpc_racing_b200.pipeline import SolvePipeline
-    mkpipe = lambda host_side: SolvePipeline(depth=2, device=local, host=host_side, N=N, Ts=TS, model=cfg["model"],
+    mkpipe = lambda host_side: SolvePipeline(depth=max(1, args.pipeline_depth), device=local, host=host_side, N=N, Ts=TS, model=cfg["model"],
                                              lane_constraint=cfg["lane"], restoration=True)
     pipe = mkpipe(False)
     psub = lambda: pipe.submit(din["x0"], din["u_prev"], din["s0"], din["cx"], din["cy"], max_err=din.get("max_err"))
-    for _ in range(2):
+    for _ in range(max(2, args.pipeline_depth)):
         psub()
     pipe.drain()
     _barrier(torch, dist, world, dev)
@@ -474,11 +480,11 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         return hsolver.solve(p["x0"], p["u_prev"], p["s0"], p["cx"], p["cy"], max_err=p.get("max_err"), out=o)
 
     hsolve(pin, hout)
-    # the same two-deep pipeline through the C ABI with host arrays (mpcr_solve_batch_async): the copies of
+    # the same pipeline through the C ABI with host arrays (mpcr_solve_batch_async): the copies of
     # one step overlap the kernels of the other; every step's inputs go H2D and its results D2H
     hpipe = mkpipe(True)
     hsub = lambda: hpipe.submit(pin["x0"], pin["u_prev"], pin["s0"], pin["cx"], pin["cy"], max_err=pin.get("max_err"))
-    for _ in range(2):
+    for _ in range(max(2, args.pipeline_depth)):
         hsub()
     hpipe.drain()
     _barrier(torch, dist, world, dev)
@@ -597,14 +603,15 @@ def run_gpu_solve(args, cfg, torch, dist, world, rank, local, dev, pinned):
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_block(args.config, cfg, args.batch if args.scaling == "weak" else B, args.scaling),
-        "value_is": "restoration phase ON (the drop-in MPC class's options); the K steps go through a two-deep "
-                    "pipeline (two handles on two streams, mpc_racing_b200/pipeline.py): the tail of one launch overlaps "
+        "value_is": "restoration phase ON (the drop-in MPC class's options); the K steps go through a "
+                    f"{max(1, args.pipeline_depth)}-deep pipeline (one handle and stream per slot, mpc_racing_b200/pipeline.py): the tail of one launch overlaps "
                     "the head of the next.  `serial` = one launch at a time, each step timed on its own",
         "serial": {"value": conv_all / (float(per_rank[:, 8].max()) * 1e-3), "unit": UNIT,
                    "ms_per_step": float(per_rank[:, 8].max()),
                    "note": "max over ranks of the mean serial step; kernel_ms and the roofline are measured on these launches"},
         "detail": {"l2": "flushed before every timed step (256 MB write on the step's stream, inside the timed region)",
                    "pipeline_results_bit_identical_to_serial": pipeline_identical and e2e_identical,
+                   "pipeline_depth": max(1, args.pipeline_depth),
                    "converged_frac": conv_all / b_all, "mean_iters": float(iters.mean()), "launch": launch,
                    "host_affinity": pinned},
         "no_restoration": {"value": plain_conv_all / (float(per_rank[:, 3].max()) * 1e-3), "unit": UNIT,
@@ -638,7 +645,7 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
     if cfg["kind"] == "rollout" and args.scaling == "strong":
         lo, hi = shard_range(args.batch, rank, world)
         R = hi - lo
-    groups, total = rollout_starts(cfg, R, rank, world)
+    groups, total = rollout_starts(cfg, R, rank, world, split=max(1, args.engines_per_track))
     engines = []
     for track, n, prm, seed in groups:
         cl = ParameterizedCenterline(track, lanes=False, error=False, device=local)
@@ -775,6 +782,10 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--inner", type=int, default=20, help="control steps per bench step (cfg4 / cfg5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=3,
+                    help="cfg2 / cfg3: handles (streams) of the solve pipeline; 1 = one launch at a time")
+    ap.add_argument("--engines-per-track", type=int, default=1,
+                    help="cfg4: independent sub-fleets per track, each on its own stream")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
