@@ -237,7 +237,7 @@ class CpuClosedLoop:
         return conv
 
 
-def rollout_starts(cfg, R, rank=0, world=1, split=1):
+def rollout_starts(cfg, R, rank=0, world=1):
     """Start states of config 4 / 5: per track, s0 ~ U[0, L) on the centerline, tangent yaw, v0 = 5."""
     from mpc_racing_b200.sharding import shard_range
     tracks = cfg["tracks"]
@@ -256,13 +256,7 @@ def rollout_starts(cfg, R, rank=0, world=1, split=1):
         return out, len(pairs)
     per = R // len(tracks)
     for j, t in enumerate(tracks):
-        n = per if j < len(tracks) - 1 else R - per * (len(tracks) - 1)
-        # `split` engines per track: sub-fleets on their own streams, so that the tail of one engine's
-        # solve launch is filled by the others (same idea as the solve pipeline; the fleets are independent)
-        for q in range(split):
-            lo, hi = shard_range(n, q, split)
-            if hi > lo:
-                out.append((t, hi - lo, None, 1234 + 17 * rank + j + 1000 * q))
+        out.append((t, per if j < len(tracks) - 1 else R - per * (len(tracks) - 1), None, 1234 + 17 * rank + j))
     return out, R
 
 
@@ -645,14 +639,22 @@ def run_gpu_rollout(args, cfg, torch, dist, world, rank, local, dev, pinned):
     if cfg["kind"] == "rollout" and args.scaling == "strong":
         lo, hi = shard_range(args.batch, rank, world)
         R = hi - lo
-    groups, total = rollout_starts(cfg, R, rank, world, split=max(1, args.engines_per_track))
+    groups, total = rollout_starts(cfg, R, rank, world)
+    split = max(1, args.engines_per_track)
     engines = []
     for track, n, prm, seed in groups:
         cl = ParameterizedCenterline(track, lanes=False, error=False, device=local)
-        ro = ClosedLoopRollouts(cl, N=cfg["N"], Ts=TS, nlp_model=cfg["model"], plant=cfg["plant"], device=local,
-                                restoration=True)
         x0, s0 = start_states(cl, n, seed=seed, v0=5.0)
-        engines.append(dict(ro=ro, x0=x0, s0=s0, prm=prm, n=n, track=track))
+        # --engines-per-track: the track's fleet as independent sub-fleets (same vehicles), each engine on its
+        # own stream, so that the tail of one engine's solve launch is filled by the others
+        for q in range(split):
+            lo, hi = shard_range(n, q, split)
+            if hi <= lo:
+                continue
+            ro = ClosedLoopRollouts(cl, N=cfg["N"], Ts=TS, nlp_model=cfg["model"], plant=cfg["plant"], device=local,
+                                    restoration=True)
+            engines.append(dict(ro=ro, x0=x0[lo:hi], s0=s0[lo:hi], prm=None if prm is None else prm[lo:hi],
+                                n=hi - lo, track=track))
     K = args.inner
     fit_local = None
 
