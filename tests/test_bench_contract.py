@@ -32,6 +32,24 @@ def test_reference_arm_other_ranks_exit_quietly():
 import pytest
 
 
+def test_clock_summary_of_one_and_several_gpus():
+    """`clocks`: rank 0's GPU in the contract's keys, every GPU of the job under `per_gpu`, throttle
+    reasons collected over all of them."""
+    sys.path.insert(0, ROOT)
+    import bench
+    row = lambda mhz, cap, w, t: [str(mhz), "1965", "Not Active", "Not Active", "Not Active", cap, str(w), str(t)]
+    one = bench.summarize_clocks([[row(1965, "Not Active", 350.5, 41)] for _ in range(4)])
+    assert one["sm_mhz"] == 1965.0 and one["sm_max_mhz"] == 1965.0 and one["reasons"] == [] and one["samples"] == 4
+    assert one["power_w"] == 350.5 and "per_gpu" not in one
+    two = bench.summarize_clocks([[row(1965, "Not Active", 300, 40), row(1800, "Active", 700, 70)] for _ in range(3)])
+    assert two["sm_mhz"] == 1965.0 and two["reasons"] == ["sw_power_cap"]
+    assert [g["sm_mhz"] for g in two["per_gpu"]] == [1965.0, 1800.0] and two["per_gpu"][1]["reasons"] == ["sw_power_cap"]
+    none = bench.summarize_clocks([])
+    assert none["sm_mhz"] is None and none["reasons"] == ["nvidia-smi unavailable"]
+    odd = bench.summarize_clocks([[["[N/A]", "[N/A]", "Not Active", "Not Active", "Not Active", "Not Active", "[N/A]", "40"]]])
+    assert odd["sm_mhz"] is None and odd["reasons"] == []
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("config", ["cfg2", "cfg4"])
 def test_gpu_arm_json_line(config):
