@@ -2,7 +2,7 @@
 oracle (oracle/cxx) run on the box's host cores with the same options - plain and polished
 (polish_tol = 1e-9 on both sides).  Prints the parity table of DESIGN.md and the outlier lists.
 
-    python tools/parity_report.py [polish_tol]
+    python tests/parity_report.py [polish_tol]
 """
 import json
 import os

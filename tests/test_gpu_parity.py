@@ -176,7 +176,7 @@ def test_whole_batches_against_oracle_golden(name, kw, N):
     restoration phase) and the production batch (256, N = 15) against the committed oracle solutions
     (tests/golden/*_oracle.npz, generator make_oracle_solutions.py).  Kernel (Riccati + Woodbury) and
     oracle (dense LDL') follow the same algorithm but not the same round-off.  Measured on B200, round 2
-    (tools/parity_report.py, DESIGN.md "Parity status"): converged / failed class equal 100 % on every
+    (tests/parity_report.py, DESIGN.md "Parity status"): converged / failed class equal 100 % on every
     batch, objective within 1e-6 on 100 %, inputs within 1e-4 on 99.90 % / 100 % / 100 % / 100 % - the
     config-2 rest are 4 problems (245, 910, 1622, 3231) with the objective equal to 1e-6 and one
     throttle component off by up to 5.7e-3: a direction the tol = 1e-4 termination leaves undetermined."""
